@@ -1,0 +1,200 @@
+"""ctypes binding of the C-ABI kernel library (``include/frl_b200.h``).
+
+There is no fallback: if ``csrc/libfrl_b200.so`` is missing or a launch fails this module
+raises.  ``python __graft_entry__.py build`` (or ``make -C csrc``) produces the library in-tree.
+"""
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC_DIR, "libfrl_b200.so")
+
+F32, BF16, U8, I64 = 0, 1, 2, 3
+LOSS_MSE, LOSS_CE = 0, 1
+MAX_TASKS = 8
+
+_DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: U8, torch.bool: U8,
+               torch.int64: I64}
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class TaskDesc(C.Structure):
+    """Mirror of ``frl_task_desc``."""
+    _fields_ = [
+        ("kind", C.c_int32), ("out_dtype", C.c_int32), ("tgt_dtype", C.c_int32),
+        ("ignore_index", C.c_int32),
+        ("out", C.c_void_p), ("tgt", C.c_void_p), ("mask", C.c_void_p), ("dout", C.c_void_p),
+        ("rows", C.c_int64), ("cols", C.c_int64), ("mask_inner", C.c_int64),
+        ("weight", C.c_float), ("_pad", C.c_float),
+    ]
+
+
+# name -> (restype, argtypes); every name here must be declared in include/frl_b200.h
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+SIGNATURES = {
+    "frl_abi_version": (_i, []),
+    "frl_last_error": (C.c_char_p, []),
+    "frl_launch_count": (C.c_uint64, []),
+    "frl_launch_count_reset": (None, []),
+    "frl_device_sm_count": (_i, []),
+    "frl_device_arch": (_i, []),
+    "frl_sgd_momentum": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _vp, _i, _i, _vp]),
+    "frl_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i64, _f, _vp, _i, _vp]),
+    "frl_rmsprop": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _vp, _i, _vp]),
+    "frl_reduce_scratch_bytes": (_i64, []),
+    "frl_grad_sumsq_clip": (_i, [_vp, _i64, _i, _f, _f, _vp, _vp, _vp]),
+    "frl_criteria_scratch_bytes": (_i64, [_i]),
+    "frl_criteria_forward": (_i, [C.POINTER(TaskDesc), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "frl_criteria_backward": (_i, [C.POINTER(TaskDesc), _i, _vp, _vp, _vp, _vp]),
+    "frl_preproc_affine": (_i, [_vp, _i, _vp, _i, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "frl_cast_scale": (_i, [_vp, _i, _vp, _i, _i64, _f, _vp]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the library in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC_DIR, "-j8"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise NativeLibraryError("building libfrl_b200.so failed:\n" + res.stderr[-4000:])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} is missing: the sm_100a kernel library has not been built "
+                "(run `python __graft_entry__.py build` or `make -C <pkg>/csrc`). "
+                "There is no fallback path.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)        # AttributeError if the .so is stale
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if handle.frl_abi_version() != 1:
+            raise NativeLibraryError("libfrl_b200.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def is_available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().frl_last_error().decode("utf-8", "replace")
+        raise NativeLibraryError(f"{what} failed (rc={rc}): {msg}")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPE_CODE[dt]
+    except KeyError:
+        raise NativeLibraryError(f"dtype {dt} has no kernel path") from None
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().frl_launch_count())
+
+
+def launch_count_reset() -> None:
+    lib().frl_launch_count_reset()
+
+
+# ---- K2 -------------------------------------------------------------------------------------
+
+def sgd_momentum(p, g, buf, p_lp, n, *, lr, mu, dampening, wd, grad_scale=1.0,
+                 grad_scale_dev=None, first_step=False) -> None:
+    _check(lib().frl_sgd_momentum(_ptr(p), _ptr(g), _ptr(buf), _ptr(p_lp), n, lr, mu, dampening,
+                                  wd, grad_scale, _ptr(grad_scale_dev), int(first_step),
+                                  dtype_code(g.dtype), _stream()), "frl_sgd_momentum")
+
+
+def adam(p, g, m, v, vmax, p_lp, n, *, lr, beta1, beta2, eps, wd, step, grad_scale=1.0,
+         grad_scale_dev=None) -> None:
+    _check(lib().frl_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(vmax), _ptr(p_lp), n, lr,
+                          beta1, beta2, eps, wd, step, grad_scale, _ptr(grad_scale_dev),
+                          dtype_code(g.dtype), _stream()), "frl_adam")
+
+
+def rmsprop(p, g, sq, buf, p_lp, n, *, lr, alpha, eps, wd, mu, grad_scale=1.0,
+            grad_scale_dev=None) -> None:
+    _check(lib().frl_rmsprop(_ptr(p), _ptr(g), _ptr(sq), _ptr(buf), _ptr(p_lp), n, lr, alpha,
+                             eps, wd, mu, grad_scale, _ptr(grad_scale_dev),
+                             dtype_code(g.dtype), _stream()), "frl_rmsprop")
+
+
+# ---- K3 -------------------------------------------------------------------------------------
+
+def reduce_scratch_bytes() -> int:
+    return int(lib().frl_reduce_scratch_bytes())
+
+
+def grad_sumsq_clip(g, n, *, pre_scale, max_norm, out3, scratch) -> None:
+    _check(lib().frl_grad_sumsq_clip(_ptr(g), n, dtype_code(g.dtype), pre_scale, max_norm,
+                                     _ptr(out3), _ptr(scratch), _stream()), "frl_grad_sumsq_clip")
+
+
+# ---- K4 -------------------------------------------------------------------------------------
+
+def criteria_scratch_bytes(n_tasks: int) -> int:
+    return int(lib().frl_criteria_scratch_bytes(n_tasks))
+
+
+def make_task_array(descs: Sequence[TaskDesc]):
+    arr = (TaskDesc * len(descs))()
+    for i, d in enumerate(descs):
+        arr[i] = d
+    return arr
+
+
+def criteria_forward(task_array, n_tasks, losses, aux, lse, sink, nan_flag, scratch) -> None:
+    _check(lib().frl_criteria_forward(task_array, n_tasks, _ptr(losses), _ptr(aux), _ptr(lse),
+                                      _ptr(sink), _ptr(nan_flag), _ptr(scratch), _stream()),
+           "frl_criteria_forward")
+
+
+def criteria_backward(task_array, n_tasks, grad_losses, aux, lse) -> None:
+    _check(lib().frl_criteria_backward(task_array, n_tasks, _ptr(grad_losses), _ptr(aux),
+                                       _ptr(lse), _stream()), "frl_criteria_backward")
+
+
+# ---- K5 -------------------------------------------------------------------------------------
+
+def preproc_affine(src, dst, *, inner=1, channels=1, scale=None, bias=None) -> None:
+    n = src.numel()
+    assert dst.numel() == n and src.is_contiguous() and dst.is_contiguous()
+    _check(lib().frl_preproc_affine(_ptr(src), dtype_code(src.dtype), _ptr(dst),
+                                    dtype_code(dst.dtype), n, inner, channels, _ptr(scale),
+                                    _ptr(bias), _stream()), "frl_preproc_affine")
+
+
+def cast_scale(src, dst, scale: float = 1.0) -> None:
+    n = src.numel()
+    assert dst.numel() == n and src.is_contiguous() and dst.is_contiguous()
+    _check(lib().frl_cast_scale(_ptr(src), dtype_code(src.dtype), _ptr(dst),
+                                dtype_code(dst.dtype), n, scale, _stream()), "frl_cast_scale")

@@ -1,0 +1,261 @@
+// K2 — fused optimizer update over a flat bucket of the parameter arena (sm_100a).
+//
+// One streaming pass: read the (already all-reduced) gradient bucket, the fp32 master weights
+// and the optimizer state; apply torch 2.11's update rule in fp32; write master, state and —
+// in bf16 mode — the bf16 shadow weights the next forward reads.  Gradient scaling (1/world,
+// clip coefficient) is folded into the gradient read, so the flatten / pre-divide / copy-out
+// passes of the stock DDP reducer do not exist here.
+//
+// HBM-bound: 20 B/param (SGD-momentum), 28 B/param (Adam, RMSprop+momentum), 36 B/param
+// (Adam+amsgrad); +2 B with a bf16 shadow, -2 B with a bf16 gradient.
+//
+// Layout: every thread owns 4 consecutive elements per item, so fp32 arrays move as fully
+// coalesced 16-byte accesses (bf16 as 8-byte).  Each thread issues the loads of UNROLL items
+// before the first use (UNROLL * (2 + NSTATE) independent 128-bit loads in flight), which is
+// what keeps ~100 KB per SM outstanding — the amount Little's law asks for at ~6.5 TB/s.
+#include "frl_common.cuh"
+
+namespace frl {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+constexpr int kTileVec = kThreads * kUnroll;   // vec4 items per tile
+
+// ---- update rules (scalar, fp32) ------------------------------------------------------------
+struct SgdRule {
+    float neg_lr, mu, one_minus_damp, wd;
+    int first_step, has_buf;
+    static constexpr int kStates = 1;
+    __device__ __forceinline__ void operator()(float& p, float g, float& buf, float&, float&) const {
+        g = fmaf(wd, p, g);
+        if (has_buf) {
+            buf = first_step ? g : fmaf(mu, buf, one_minus_damp * g);
+            g = buf;
+        }
+        p = fmaf(neg_lr, g, p);
+    }
+};
+
+template <bool AMSGRAD>
+struct AdamRule {
+    float w1;               // 1 - beta1   (lerp weight)
+    float beta2, w2;        // beta2, 1 - beta2
+    float eps, wd;
+    float neg_step_size;    // -lr / (1 - beta1^t)
+    float bc2_sqrt;         // sqrt(1 - beta2^t)
+    static constexpr int kStates = AMSGRAD ? 3 : 2;
+    __device__ __forceinline__ void operator()(float& p, float g, float& m, float& v, float& vmax) const {
+        g = fmaf(wd, p, g);
+        m = fmaf(w1, g - m, m);                       // exp_avg.lerp_(g, 1-beta1), weight < 0.5 branch
+        v = fmaf(w2 * g, g, v * beta2);               // mul_(beta2).addcmul_(g, g, 1-beta2)
+        float vv = v;
+        if (AMSGRAD) { vmax = fmaxf(vmax, v); vv = vmax; }
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        p = fmaf(neg_step_size, m / denom, p);        // addcdiv_(m, denom, -step_size)
+    }
+};
+
+template <bool MOMENTUM>
+struct RmspropRule {
+    float alpha, one_minus_alpha, eps, wd, mu, neg_lr;
+    static constexpr int kStates = MOMENTUM ? 2 : 1;
+    __device__ __forceinline__ void operator()(float& p, float g, float& sq, float& buf, float&) const {
+        g = fmaf(wd, p, g);
+        sq = fmaf(one_minus_alpha * g, g, sq * alpha);
+        const float avg = sqrtf(sq) + eps;
+        float upd = g / avg;
+        if (MOMENTUM) { buf = fmaf(mu, buf, upd); upd = buf; }
+        p = fmaf(neg_lr, upd, p);
+    }
+};
+
+// ---- gradient vector load (scaled, as fp32) ---------------------------------------------------
+__device__ __forceinline__ f32x4 load_grad4(const f32x4* g, int64_t i) { return ld_stream_ro(g + i); }
+__device__ __forceinline__ f32x4 load_grad4(const bf16x4* g, int64_t i) {
+    const bf16x4 r = ld_stream_ro(g + i);
+    return f32x4{bf16lo(r.a), bf16hi(r.a), bf16lo(r.b), bf16hi(r.b)};
+}
+__device__ __forceinline__ float load_grad1(const f32x4* g, int64_t e) {
+    return reinterpret_cast<const float*>(g)[e];
+}
+__device__ __forceinline__ float load_grad1(const bf16x4* g, int64_t e) {
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g)[e]);
+}
+
+template <typename Rule>
+__device__ __forceinline__ void apply4(const Rule& r, f32x4& p, const f32x4& g, float gs,
+                                       f32x4& s0, f32x4& s1, f32x4& s2) {
+    r(p.x, g.x * gs, s0.x, s1.x, s2.x);
+    r(p.y, g.y * gs, s0.y, s1.y, s2.y);
+    r(p.z, g.z * gs, s0.z, s1.z, s2.z);
+    r(p.w, g.w * gs, s0.w, s1.w, s2.w);
+}
+
+// NS = number of state arrays actually touched (0..3).
+template <typename Rule, typename GVec, int NS, bool HAS_LP>
+__global__ void __launch_bounds__(kThreads)
+update_kernel(float* __restrict__ p_, const GVec* __restrict__ g, float* __restrict__ s0_,
+              float* __restrict__ s1_, float* __restrict__ s2_, bf16x4* __restrict__ lp,
+              int64_t n, Rule rule, float gscale, const float* __restrict__ gscale_dev) {
+    f32x4* p = reinterpret_cast<f32x4*>(p_);
+    f32x4* s0 = reinterpret_cast<f32x4*>(s0_);
+    f32x4* s1 = reinterpret_cast<f32x4*>(s1_);
+    f32x4* s2 = reinterpret_cast<f32x4*>(s2_);
+    const float gs = gscale_dev ? gscale * __ldg(gscale_dev) : gscale;
+    const int64_t n_vec = n >> 2;
+    const int64_t n_tiles = (n_vec + kTileVec - 1) / kTileVec;
+    const f32x4 zero{0.f, 0.f, 0.f, 0.f};
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * kTileVec + threadIdx.x;
+        f32x4 vp[kUnroll], vg[kUnroll], a0[kUnroll], a1[kUnroll], a2[kUnroll];
+        if (base + (kUnroll - 1) * kThreads < n_vec) {      // whole tile in range for this thread
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                const int64_t i = base + j * kThreads;
+                vg[j] = load_grad4(g, i);
+                vp[j] = ld_stream(p + i);
+                a0[j] = NS > 0 ? ld_stream(s0 + i) : zero;
+                a1[j] = NS > 1 ? ld_stream(s1 + i) : zero;
+                a2[j] = NS > 2 ? ld_stream(s2 + i) : zero;
+            }
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                const int64_t i = base + j * kThreads;
+                apply4(rule, vp[j], vg[j], gs, a0[j], a1[j], a2[j]);
+                st_stream(p + i, vp[j]);
+                if (NS > 0) st_stream(s0 + i, a0[j]);
+                if (NS > 1) st_stream(s1 + i, a1[j]);
+                if (NS > 2) st_stream(s2 + i, a2[j]);
+                if (HAS_LP) st_stream(lp + i, bf16x4{pack_bf16(vp[j].x, vp[j].y), pack_bf16(vp[j].z, vp[j].w)});
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                const int64_t i = base + j * kThreads;
+                if (i >= n_vec) break;
+                f32x4 qg = load_grad4(g, i), qp = ld_stream(p + i);
+                f32x4 q0 = NS > 0 ? ld_stream(s0 + i) : zero;
+                f32x4 q1 = NS > 1 ? ld_stream(s1 + i) : zero;
+                f32x4 q2 = NS > 2 ? ld_stream(s2 + i) : zero;
+                apply4(rule, qp, qg, gs, q0, q1, q2);
+                st_stream(p + i, qp);
+                if (NS > 0) st_stream(s0 + i, q0);
+                if (NS > 1) st_stream(s1 + i, q1);
+                if (NS > 2) st_stream(s2 + i, q2);
+                if (HAS_LP) st_stream(lp + i, bf16x4{pack_bf16(qp.x, qp.y), pack_bf16(qp.z, qp.w)});
+            }
+        }
+    }
+    // scalar tail: n % 4 trailing elements
+    const int64_t tail0 = n_vec << 2;
+    if (blockIdx.x == 0 && tail0 + threadIdx.x < n) {
+        const int64_t e = tail0 + threadIdx.x;
+        float pe = p_[e], d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        if (NS > 0) d0 = s0_[e];
+        if (NS > 1) d1 = s1_[e];
+        if (NS > 2) d2 = s2_[e];
+        rule(pe, load_grad1(g, e) * gs, d0, d1, d2);
+        p_[e] = pe;
+        if (NS > 0) s0_[e] = d0;
+        if (NS > 1) s1_[e] = d1;
+        if (NS > 2) s2_[e] = d2;
+        if (HAS_LP) reinterpret_cast<__nv_bfloat16*>(lp)[e] = __float2bfloat16_rn(pe);
+    }
+}
+
+// grid: one resident wave — (CTAs that fit per SM for this instantiation) x SM count, capped by
+// the number of tiles; the grid-stride loop walks the rest, so there is no partial last wave.
+template <typename K>
+static int grid_for(K kernel, int64_t n) {
+    static int occ = 0;            // per template instantiation
+    if (occ == 0) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, kThreads, 0) != cudaSuccess || o < 1) o = 2;
+        occ = o;
+    }
+    const int64_t tiles = (n / 4 + kTileVec - 1) / kTileVec;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * occ;
+    int64_t g = tiles < cap ? tiles : cap;
+    return g < 1 ? 1 : static_cast<int>(g);
+}
+
+template <typename Rule, int NS>
+static int launch_update(const Rule& rule, float* p, const void* g, float* s0, float* s1, float* s2,
+                         void* p_lp, int64_t n, float gscale, const float* gscale_dev,
+                         int g_dtype, cudaStream_t st, const char* name) {
+    FRL_REQUIRE(n >= 0, FRL_E_ARG, "%s: n < 0", name);
+    if (n == 0) return 0;
+    FRL_REQUIRE(p && g, FRL_E_ARG, "%s: null p/g", name);
+    FRL_REQUIRE(g_dtype == FRL_F32 || g_dtype == FRL_BF16, FRL_E_DTYPE, "%s: g_dtype %d", name, g_dtype);
+    FRL_REQUIRE(aligned16(p) && aligned16(g) && aligned16(s0) && aligned16(s1) && aligned16(s2) &&
+                aligned16(p_lp), FRL_E_ALIGN, "%s: arrays must be 16-byte aligned", name);
+    bf16x4* lp = static_cast<bf16x4*>(p_lp);
+#define FRL_LAUNCH(GV, LP)                                                                      \
+    update_kernel<Rule, GV, NS, LP><<<grid_for(update_kernel<Rule, GV, NS, LP>, n), kThreads, 0, st>>>( \
+        p, static_cast<const GV*>(g), s0, s1, s2, lp, n, rule, gscale, gscale_dev)
+    if (g_dtype == FRL_F32) { if (lp) FRL_LAUNCH(f32x4, true); else FRL_LAUNCH(f32x4, false); }
+    else                    { if (lp) FRL_LAUNCH(bf16x4, true); else FRL_LAUNCH(bf16x4, false); }
+#undef FRL_LAUNCH
+    return after_launch(name);
+}
+
+}  // namespace frl
+
+using namespace frl;
+
+extern "C" int frl_sgd_momentum(float* p, const void* g, float* buf, void* p_lp, int64_t n,
+                                float lr, float mu, float dampening, float wd,
+                                float grad_scale, const float* grad_scale_dev,
+                                int first_step, int g_dtype, void* stream) {
+    FRL_REQUIRE(mu == 0.f || buf != nullptr, FRL_E_ARG, "frl_sgd_momentum: momentum needs buf");
+    SgdRule r{-lr, mu, 1.f - dampening, wd, first_step ? 1 : 0, (mu != 0.f) ? 1 : 0};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mu != 0.f)
+        return launch_update<SgdRule, 1>(r, p, g, buf, nullptr, nullptr, p_lp, n, grad_scale,
+                                         grad_scale_dev, g_dtype, st, "frl_sgd_momentum");
+    return launch_update<SgdRule, 0>(r, p, g, nullptr, nullptr, nullptr, p_lp, n, grad_scale,
+                                     grad_scale_dev, g_dtype, st, "frl_sgd_momentum");
+}
+
+extern "C" int frl_adam(float* p, const void* g, float* m, float* v, float* vmax, void* p_lp,
+                        int64_t n, float lr, float beta1, float beta2, float eps, float wd,
+                        int64_t step, float grad_scale, const float* grad_scale_dev,
+                        int g_dtype, void* stream) {
+    FRL_REQUIRE(m && v, FRL_E_ARG, "frl_adam: null state");
+    FRL_REQUIRE(step >= 1, FRL_E_ARG, "frl_adam: step must be >= 1");
+    // bias corrections in double, as torch computes them from Python floats
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+    const float neg_step = static_cast<float>(-(static_cast<double>(lr) / bc1));
+    const float bc2s = static_cast<float>(sqrt(bc2));
+    const float w1 = static_cast<float>(1.0 - static_cast<double>(beta1));
+    const float w2 = static_cast<float>(1.0 - static_cast<double>(beta2));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (vmax) {
+        AdamRule<true> r{w1, beta2, w2, eps, wd, neg_step, bc2s};
+        return launch_update<AdamRule<true>, 3>(r, p, g, m, v, vmax, p_lp, n, grad_scale,
+                                                grad_scale_dev, g_dtype, st, "frl_adam");
+    }
+    AdamRule<false> r{w1, beta2, w2, eps, wd, neg_step, bc2s};
+    return launch_update<AdamRule<false>, 2>(r, p, g, m, v, nullptr, p_lp, n, grad_scale,
+                                             grad_scale_dev, g_dtype, st, "frl_adam");
+}
+
+extern "C" int frl_rmsprop(float* p, const void* g, float* sq, float* buf, void* p_lp, int64_t n,
+                           float lr, float alpha, float eps, float wd, float mu,
+                           float grad_scale, const float* grad_scale_dev, int g_dtype,
+                           void* stream) {
+    FRL_REQUIRE(sq, FRL_E_ARG, "frl_rmsprop: null sq");
+    FRL_REQUIRE(mu == 0.f || buf != nullptr, FRL_E_ARG, "frl_rmsprop: momentum needs buf");
+    const float oma = static_cast<float>(1.0 - static_cast<double>(alpha));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mu != 0.f) {
+        RmspropRule<true> r{alpha, oma, eps, wd, mu, -lr};
+        return launch_update<RmspropRule<true>, 2>(r, p, g, sq, buf, nullptr, p_lp, n, grad_scale,
+                                                   grad_scale_dev, g_dtype, st, "frl_rmsprop");
+    }
+    RmspropRule<false> r{alpha, oma, eps, wd, mu, -lr};
+    return launch_update<RmspropRule<false>, 1>(r, p, g, sq, nullptr, nullptr, p_lp, n, grad_scale,
+                                                grad_scale_dev, g_dtype, st, "frl_rmsprop");
+}

@@ -1,0 +1,263 @@
+"""Per-bucket gradient pipeline: flatten -> all-reduce -> fused update.
+
+Stands where the reference wraps the model in ``DistributedDataParallel`` (reference
+solver.py:265-294) and later calls ``clip_grad_norm_`` / ``optimizer.step()`` (reference
+solver_worker.py:585-592).  Differences that matter on B200:
+
+* gradients land in the flat ``grad`` arena as soon as autograd produces them (a
+  post-accumulate hook per parameter; ``nn.Linear`` weight gradients are written there directly
+  by ``arena_linear``), so a bucket is a contiguous slice NCCL reduces **in place** — no bucket
+  copy-in, no copy-out;
+* the 1/world mean and the clip coefficient are folded into the update kernel's gradient read;
+* each bucket's all-reduce is issued on a side stream the moment its last gradient is ready and
+  its fused update is chained right behind it, overlapping the rest of backward;
+* with clipping enabled the updates wait for the global norm (two-phase tail), computed by one
+  reduction kernel over the model range with no host sync.
+"""
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _native
+from .arena import ParamArena
+from .fused_optim import FusedArenaOptimizer
+
+KERNELS = _native     # swapped by CPU tests of the host logic
+
+
+class _Bucket:
+    __slots__ = ("lo", "hi", "slots", "pending", "work", "launched")
+
+    def __init__(self, lo: int, hi: int):
+        self.lo, self.hi = lo, hi
+        self.slots = []
+        self.pending = 0
+        self.work = None
+        self.launched = False
+
+
+class GradBucketPipeline:
+    def __init__(self, arena: ParamArena, optimizer: FusedArenaOptimizer, *,
+                 process_group=None, world_size: int = 1, clip_norm: float = 0.0,
+                 bucket_cap_mb: float = 25.0, first_bucket_mb: Optional[float] = 1.0,
+                 eager_update: bool = True) -> None:
+        self.arena = arena
+        self.optimizer = optimizer
+        self.pg = process_group
+        self.world = world_size
+        self.clip_norm = float(clip_norm or 0.0)
+        self.grad_scale = 1.0 / world_size
+        self.distributed = world_size > 1
+        # eager: update a bucket as soon as it is reduced (needs no global norm)
+        self.eager = eager_update and self.clip_norm == 0.0 and self.distributed
+        self.on_cuda = arena.device.type == "cuda"
+
+        cap = int(bucket_cap_mb * 1024 * 1024)
+        first = int(first_bucket_mb * 1024 * 1024) if (first_bucket_mb and self.distributed) else None
+        ranges = arena.buckets(cap, first) if self.distributed else [(0, arena.numel)]
+        self.buckets: List[_Bucket] = [_Bucket(lo, hi) for lo, hi in ranges]
+        self._bucket_of = {}
+        for s in arena.slots:
+            for b in self.buckets:
+                if b.lo <= s.offset < b.hi:
+                    b.slots.append(s)
+                    self._bucket_of[id(s.param)] = b
+                    break
+        self._n_slots = len(arena.slots)
+        self._ready = 0
+        self._ready_ids = set()
+        self._handles = []
+        for s in arena.slots:
+            self._handles.append(s.param.register_post_accumulate_grad_hook(self._make_hook(s)))
+
+        self.side_stream = torch.cuda.Stream(device=arena.device) if self.on_cuda else None
+        self.clip_out = None
+        self.clip_scratch = None
+        if self.clip_norm > 0.0:
+            self.clip_out = torch.zeros(3, dtype=torch.float32, device=arena.device)
+            nbytes = KERNELS.reduce_scratch_bytes()
+            self.clip_scratch = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=arena.device)
+        self._step_open = False
+        # timing taps (bench): list of (start_event, end_event, lo, hi) for update launches
+        self.record_update_events = False
+        self.update_events: List[Tuple[torch.cuda.Event, torch.cuda.Event, int, int]] = []
+
+    # -- step protocol ---------------------------------------------------------------------------
+    def begin_step(self) -> None:
+        """Call before ``backward()``."""
+        self._ready = 0
+        self._ready_ids.clear()
+        for b in self.buckets:
+            b.pending = len(b.slots)
+            b.work = None
+            b.launched = False
+        self.optimizer.begin_step()
+        self._step_open = True
+
+    def _make_hook(self, slot) -> Callable[[nn.Parameter], None]:
+        def hook(param: nn.Parameter) -> None:
+            g = param.grad
+            if g is not None:
+                dst = self.arena.grad_view(slot)
+                if g.data_ptr() != dst.data_ptr():
+                    dst.copy_(g)              # flatten (casts fp32 -> bf16 grads when needed)
+                param.grad = None             # next backward steals again instead of accumulating
+            self.mark_ready(slot)
+        return hook
+
+    def mark_ready(self, slot) -> None:
+        if not self._step_open or id(slot.param) in self._ready_ids:
+            return
+        self._ready_ids.add(id(slot.param))
+        self._ready += 1
+        b = self._bucket_of[id(slot.param)]
+        b.pending -= 1
+        if b.pending == 0 and self.distributed:
+            self._launch_bucket(b)
+
+    def _launch_bucket(self, b: _Bucket) -> None:
+        view = self.arena.grad[b.lo:b.hi]
+        if self.on_cuda:
+            self.side_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side_stream):
+                b.work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                if self.eager:
+                    b.work.wait()             # stream-level wait, host does not block
+                    self._update(b.lo, b.hi, None)
+        else:
+            b.work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            if self.eager:
+                b.work.wait()
+                self._update(b.lo, b.hi, None)
+        b.launched = True
+
+    def _update(self, lo: int, hi: int, coef) -> None:
+        if self.record_update_events and self.on_cuda:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.optimizer.apply_range(lo, hi, grad_scale=self.grad_scale, clip_coef_dev=coef)
+            e1.record()
+            self.update_events.append((e0, e1, lo, hi))
+        else:
+            self.optimizer.apply_range(lo, hi, grad_scale=self.grad_scale, clip_coef_dev=coef)
+
+    def finish_step(self) -> None:
+        """Call after ``backward()`` returned: reduces/updates whatever is still outstanding and
+        re-joins the side stream."""
+        if not self._step_open:
+            raise RuntimeError("finish_step() without begin_step()")
+        self._step_open = False
+        if self._ready != self._n_slots:
+            missing = [s.index for s in self.arena.slots if id(s.param) not in self._ready_ids]
+            if self.distributed:
+                # same contract as DDP with find_unused_parameters=False (the reference's setting)
+                raise RuntimeError(
+                    "Expected to have finished reduction for every parameter, but parameters at "
+                    f"indices {missing} did not receive a gradient in this step")
+            self._finish_partial(missing)
+            return
+        if self.distributed:
+            if self.on_cuda:
+                cur = torch.cuda.current_stream()
+                if not self.eager:
+                    with torch.cuda.stream(self.side_stream):
+                        for b in self.buckets:
+                            b.work.wait()
+                cur.wait_stream(self.side_stream)
+            else:
+                if not self.eager:
+                    for b in self.buckets:
+                        b.work.wait()
+            if not self.eager:
+                self._tail_update()
+        else:
+            self._tail_update()
+        self.optimizer.end_step()
+
+    def _tail_update(self) -> None:
+        coef = None
+        if self.clip_norm > 0.0:
+            n_model = self.arena.model_end
+            KERNELS.grad_sumsq_clip(self.arena.grad[:n_model], n_model, pre_scale=self.grad_scale,
+                                    max_norm=self.clip_norm, out3=self.clip_out,
+                                    scratch=self.clip_scratch)
+            coef = self.clip_out[2:3]
+        self._update(0, self.arena.numel, coef)
+
+    def _finish_partial(self, missing) -> None:
+        """world_size == 1 and some parameters got no gradient: torch.optim skips those (no
+        weight decay, no momentum decay), so update only the contiguous runs that did."""
+        skip = set(missing)
+        coef = None
+        if self.clip_norm > 0.0:
+            for s in self.arena.slots:
+                if s.index in skip and s.is_model:
+                    self.arena.grad[s.offset:s.end].zero_()
+            n_model = self.arena.model_end
+            KERNELS.grad_sumsq_clip(self.arena.grad[:n_model], n_model, pre_scale=self.grad_scale,
+                                    max_norm=self.clip_norm, out3=self.clip_out,
+                                    scratch=self.clip_scratch)
+            coef = self.clip_out[2:3]
+        run_lo = None
+        prev_end = None
+        for s in self.arena.slots:
+            if s.index in skip:
+                if run_lo is not None:
+                    self._update(run_lo, prev_end, coef)
+                    run_lo = None
+                continue
+            if run_lo is None:
+                run_lo = s.offset
+            prev_end = s.end
+        if run_lo is not None:
+            self._update(run_lo, prev_end, coef)
+        self.optimizer.end_step()
+
+    # -- one-time synchronisation ----------------------------------------------------------------
+    def broadcast_parameters(self, src: int = 0) -> None:
+        """Replicas start identical to rank ``src`` (DDP does this in its constructor)."""
+        if not self.distributed:
+            return
+        dist.broadcast(self.arena.master, src=src, group=self.pg)
+        self.arena.refresh_shadow()
+
+    def remove_hooks(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
+class BufferBroadcaster:
+    """Module buffers (BatchNorm statistics) follow rank 0 before every forward, as DDP's
+    ``broadcast_buffers=True`` default does for the reference — but as ONE broadcast per dtype
+    over a flat buffer arena the buffers are re-pointed into."""
+
+    def __init__(self, module: nn.Module, *, process_group=None, world_size: int = 1) -> None:
+        self.pg = process_group
+        self.enabled = world_size > 1
+        self.flat: List[torch.Tensor] = []
+        if not self.enabled:
+            return
+        by_dtype = {}
+        for buf in module.buffers():
+            by_dtype.setdefault(buf.dtype, []).append(buf)
+        for dtype, bufs in by_dtype.items():
+            total = sum(b.numel() for b in bufs)
+            if total == 0:
+                continue
+            flat = torch.empty(total, dtype=dtype, device=bufs[0].device)
+            off = 0
+            for b in bufs:
+                n = b.numel()
+                flat[off:off + n].copy_(b.reshape(-1))
+                b.data = flat[off:off + n].view(b.shape)
+                off += n
+            self.flat.append(flat)
+
+    def sync(self, src: int = 0) -> None:
+        if self.enabled:
+            for flat in self.flat:
+                dist.broadcast(flat, src=src, group=self.pg)

@@ -1,0 +1,610 @@
+"""Per-rank epoch / minibatch loop — the hot path (reference solver_worker.py:377-832).
+
+Same observable behaviour as the reference's ``SolverWorker`` (split order, train/eval modes,
+per-minibatch loss bookkeeping, amortised metric hooks, per-epoch summaries and the yielded
+``FractionalPerformanceSummary``), restructured so that a training step never synchronises the
+host with the device:
+
+* fused criterion writes ``[total, sub-losses]`` of step *k* into row *k* of a pinned,
+  device-mapped loss log; the host reads rows two steps late (NaN guard) and the whole log once
+  per split (epoch means) instead of ``2 + T`` ``.item()`` calls per step;
+* ``backward()`` deposits gradients in the flat arena, ``GradBucketPipeline`` all-reduces and
+  applies the fused optimizer update per bucket;
+* inputs arrive through pinned memory with asynchronous copies (the reference's
+  ``pin_memory=self.device == Device.GPU`` compares a ``torch.device`` with an Enum and is
+  always False, reference solver_worker.py:829);
+* one watchdog thread per split is kicked per step instead of spawning a Timer per step.
+"""
+import heapq
+import io
+import itertools
+import json
+import logging
+import random
+import time
+from collections import defaultdict
+from math import ceil
+from typing import Any, DefaultDict, Dict, Iterator, List, NamedTuple, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.utils.data
+
+from . import _native
+from .arena import ParamArena
+from .criteria import BaseParallelCriterion, GradNormWeightedCriterion
+from .fused_optim import FusedArenaOptimizer
+from .grad_sync import BufferBroadcaster, GradBucketPipeline
+from .model import MultiTaskModel
+from .problem import BatchMetrics, Ordering, Problem
+from .sampler import ScaffoldSampler
+from .storage_layers.dataset import MultifieldDataset, NullAccessor, SubsetMultifieldDataset
+from .types import Mode, Precision, RunOpts, SampleSummary, Split
+from .watchdog import StepWatchdog
+
+logger = logging.getLogger(__name__)
+
+# samples kept per split so an exported network's input/output mapping can be validated
+MODEL_CONVERSION_TEST_SAMPLE_CT: int = 2
+NAN_CHECK_LAG = 2          # steps the host may run ahead of the loss log it inspects
+
+JSON = str
+RawMetas = Dict[str, Union[torch.Tensor, List[Union[str, float]]]]
+
+
+class SingleSample(NamedTuple):
+    data: List[torch.Tensor]
+    target: List[Tuple[torch.Tensor, ...]]
+    meta: Dict[str, Any]
+    output: List[torch.Tensor]
+    metric: Dict[str, float]
+
+    # heap entries are (score, sample): never let tuple comparison fall through to tensors
+    def __lt__(self, other: Any) -> bool:
+        return False
+
+    def __gt__(self, other: Any) -> bool:
+        return False
+
+    def __eq__(self, other: Any) -> bool:
+        return False
+
+    def __ne__(self, other: Any) -> bool:
+        return True
+
+
+class SerializableSampleSummary(NamedTuple):
+    """``SampleSummary`` with the figure pre-serialised to JSON so it can cross the pipe."""
+    image: Optional[np.ndarray]
+    text: Optional[str]
+    plot: Optional[JSON] = None
+    source: Optional[str] = None
+
+
+class FractionalEpochSplitPerformanceSummary(NamedTuple):
+    nSamples: int
+    losses: Dict[str, float]
+    metrics: Dict[str, float]
+    samples: List[SerializableSampleSummary]
+    worstSamples: List[SerializableSampleSummary]
+    testIO: List[SingleSample]
+
+
+class FractionalPerformanceSummary(NamedTuple):
+    epoch: int
+    modelBuffer: bytes
+    optimizerStateBuffer: bytes
+    performance: Dict[Split, FractionalEpochSplitPerformanceSummary]
+
+
+def stack_recursive(items):
+    assert len(items) > 0
+    first = items[0]
+    if isinstance(first, Sequence) and not torch.is_tensor(first):
+        return [torch.stack([it[i] for it in items]) for i in range(len(first))]
+    return torch.stack(list(items))
+
+
+def stat_to_str(stats: Dict[str, Tuple[np.ndarray, np.ndarray]]) -> str:
+    """``{metric: (bin counts, bin values)}`` -> cumulative-fraction table."""
+    out = ""
+    for name, (counts, values) in stats.items():
+        cum = np.cumsum(counts)
+        total = cum[-1]
+        out += "\n" + name + "\n"
+        out += "".join("{:.3f}: {:.3f}\t".format(values[i], (cum[i] / total) if total != 0 else 0.0)
+                       for i in range(len(cum)))
+    return out + "\n"
+
+
+class AverageMeter:
+    def __init__(self) -> None:
+        self.val = 0.0
+        self.avg = 0.0
+        self.sum = 0.0
+        self.count = 0
+
+    def update(self, val: float, n: int = 1) -> None:
+        self.val = val
+        self.sum += val * n
+        self.count += n
+        self.avg = self.sum / self.count
+
+
+class EpochTimer:
+    def __init__(self) -> None:
+        self.batch = AverageMeter()
+        self.epoch = AverageMeter()
+
+
+class LossLog:
+    """Pinned, device-mapped ``[capacity, 1+T]`` fp32 ring the criterion kernel writes into."""
+
+    def __init__(self, n_tasks: int, capacity: int, device: torch.device) -> None:
+        self.width = 1 + n_tasks
+        self.capacity = max(capacity, 1)
+        self.on_cuda = device.type == "cuda"
+        self.rows = torch.full((self.capacity, self.width), float("inf"), dtype=torch.float32,
+                               pin_memory=self.on_cuda)
+        self.nan_flag = torch.zeros(1, dtype=torch.int32, pin_memory=self.on_cuda)
+        self.events: List[Optional[torch.cuda.Event]] = [None] * self.capacity
+
+    def row(self, step: int) -> torch.Tensor:
+        return self.rows[step % self.capacity]
+
+    def mark(self, step: int) -> None:
+        if self.on_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self.events[step % self.capacity] = ev
+
+    def wait(self, step: int) -> None:
+        ev = self.events[step % self.capacity]
+        if ev is not None:
+            ev.synchronize()
+
+
+class SamplerState:
+    """Keeps the last few minibatches on the device and folds them into per-sample metrics,
+    a random sample set and the worst-k samples (reference solver_worker.py:189-374)."""
+
+    def __init__(self, problem: Problem, n_samples: int, dataset_len: int,
+                 device: torch.device, n_vis: int) -> None:
+        self._problem = problem
+        self._device = device
+        self._n_samples = n_samples
+        self._n_vis = min(n_samples, ceil(n_vis * (n_samples / dataset_len)))
+        n_random = min(max(self._n_vis, MODEL_CONVERSION_TEST_SAMPLE_CT), n_samples)
+        self._random_indices = frozenset(random.sample(range(n_samples), n_random))
+        self._cur_samples = 0
+        self._random_samples: List[SingleSample] = []
+        self._worst_samples: List[Tuple[float, SingleSample]] = []
+        self._rankable_metric, self._ordering = problem.get_rankable_metric()
+        self._allow_non_positive_definite = ("MSE" not in self._rankable_metric
+                                             and "EucDist" not in self._rankable_metric)
+        self._metas: List[RawMetas] = []
+        self._data: List[List[torch.Tensor]] = []
+        self._targets: List[List[Tuple[torch.Tensor, ...]]] = []
+        self._outputs: List[List[torch.Tensor]] = []
+        self._data_metric: DefaultDict[str, list] = defaultdict(list)
+
+    @staticmethod
+    def _cat_metas(metas: List[RawMetas]) -> RawMetas:
+        merged: RawMetas = {}
+        for key, first in metas[0].items():
+            vals = [m[key] for m in metas]
+            if torch.is_tensor(first):
+                merged[key] = torch.cat(vals)
+            elif isinstance(first, list):
+                merged[key] = list(itertools.chain.from_iterable(vals))
+            else:
+                raise ValueError("Unsure how to concatenate meta field with type %s" % type(first))
+        return merged
+
+    def append_sample(self, raw_metas: RawMetas, data, *, outputs, targets) -> None:
+        self._metas.append(raw_metas)
+        self._data.append([t.detach() for t in data])
+        self._outputs.append([t.detach() for t in outputs])
+        self._targets.append([tuple(t.detach() for t in head) for head in targets])
+
+    @staticmethod
+    def _one(i, data, target, output, meta, sample_metric) -> SingleSample:
+        return SingleSample(
+            data=[t[i].cpu() for t in data],
+            target=[tuple(t[i].cpu() for t in head) for head in target],
+            meta={k: None if v is None else v[i] for k, v in meta._asdict().items()},
+            output=[t[i].float().cpu() for t in output],
+            metric={k: v[i] for k, v in sample_metric.items()})
+
+    def compute_metrics(self) -> None:
+        if not self._data:
+            return
+        meta = self._problem.refine_batch_meta(self._cat_metas(self._metas))
+        n_heads = len(self._outputs[0])
+        target = [tuple(torch.cat([t[h][j] for t in self._targets])
+                        for j in range(len(self._targets[0][h]))) for h in range(n_heads)]
+        output = [torch.cat([o[h] for o in self._outputs]) for h in range(n_heads)]
+        output = [o.float() if o.dtype == torch.bfloat16 else o for o in output]
+        data = [torch.cat([d[i] for d in self._data]) for i in range(len(self._data[0]))]
+        n_group = len(data[0])
+
+        sample_metric = self._problem.compute_batch_metrics(
+            meta=meta, target=target, output=output, device=self._device)
+        if sample_metric is not None:
+            for k, v in sample_metric.items():
+                self._data_metric[k] += list(v)
+
+        if self._n_vis > 0 and sample_metric is not None:
+            base = self._cur_samples
+            for i in sorted(j - base for j in self._random_indices if base <= j < base + n_group):
+                self._random_samples.append(self._one(i, data, target, output, meta, sample_metric))
+            # worst-k: only the k most extreme samples of this group can enter the heap
+            scores = np.asarray(sample_metric[self._rankable_metric], dtype=np.float64).copy()
+            valid = np.ones(n_group, dtype=bool) if self._allow_non_positive_definite else scores >= 0
+            if self._ordering == Ordering.DESC:
+                scores = -scores
+            cand = np.flatnonzero(valid)
+            if len(cand) > self._n_vis:
+                top = np.argpartition(scores[cand], len(cand) - self._n_vis)[-self._n_vis:]
+                cand = np.sort(cand[top])
+            for i in cand:
+                score = float(scores[i])
+                if len(self._worst_samples) < self._n_vis:
+                    heapq.heappush(self._worst_samples,
+                                   (score, self._one(int(i), data, target, output, meta, sample_metric)))
+                elif score > self._worst_samples[0][0]:
+                    heapq.heappushpop(self._worst_samples,
+                                      (score, self._one(int(i), data, target, output, meta, sample_metric)))
+        self._cur_samples += n_group
+        self._metas, self._data, self._outputs, self._targets = [], [], [], []
+
+    @property
+    def n_samples(self) -> int:
+        return self._n_samples
+
+    @property
+    def random_samples(self) -> List[SingleSample]:
+        return self._random_samples
+
+    @property
+    def worst_samples(self) -> List[SingleSample]:
+        return [s for _, s in self._worst_samples]
+
+    @property
+    def data_metric(self) -> Dict[str, np.ndarray]:
+        return self._data_metric
+
+
+class SolverWorker:
+    def __init__(self, model: torch.nn.Module, criterion: BaseParallelCriterion,
+                 optimizer: FusedArenaOptimizer, device: torch.device, run_opts: RunOpts,
+                 cache=None, *, local_rank: int, node_idx: int, node_count: int,
+                 pipeline: Optional[GradBucketPipeline] = None,
+                 buffers: Optional[BufferBroadcaster] = None,
+                 precision: Precision = Precision.FP32,
+                 serialize_state: bool = True) -> None:
+        self.model = model
+        self.criterion = criterion
+        self.optimizer = optimizer
+        self.device = device
+        self.run_opts = run_opts
+        self.precision = precision
+        self.accessor = NullAccessor(process_idx=local_rank)
+        self.arena: ParamArena = optimizer.arena
+        self.pipeline = pipeline or GradBucketPipeline(
+            self.arena, optimizer, clip_norm=run_opts.optim.gradientClip)
+        self.buffers = buffers
+        self.cur_epoch = 0
+        self._node_idx = node_idx
+        self._node_count = node_count
+        self._local_rank = local_rank
+        self._serialize_state = serialize_state
+        self._state_wanted = True      # False for epochs whose state the parent will not save
+        self.save_every = 1
+        self.optimizer.zero_grad()
+        if device.type == "cuda":
+            import torch.backends.cudnn as cudnn
+            cudnn.benchmark = True
+            if precision == Precision.FP32:
+                # parity mode: plain fp32 contractions (TF32 is on by default for convolutions)
+                torch.backends.cuda.matmul.allow_tf32 = False
+                cudnn.allow_tf32 = False
+
+    # ------------------------------------------------------------------------------------------
+    # one epoch over every split
+    # ------------------------------------------------------------------------------------------
+    def _pass_one_epoch(self, problem: Problem, loaders: Dict[Split, Any], mode: Mode
+                        ) -> Dict[Split, FractionalEpochSplitPerformanceSummary]:
+        epoch_stats: Dict[Split, FractionalEpochSplitPerformanceSummary] = {}
+        names = list(self.criterion.loss_names)
+        n_tasks = len(names)
+        avg_grad_contributions = [0.0] * n_tasks
+        contribution_count = 0
+        amort = self.run_opts.metricAmortizationSchedule
+        log_freq = self.run_opts.lossLoggingFreq
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+
+        for data_type, loader in loaders.items():
+            if dist_on:
+                loader.sampler.set_epoch(self.cur_epoch)
+            # the planned order goes to the (null) cache accessor; drawing it also keeps the
+            # global RNG stream identical to the reference's (solver_worker.py:431)
+            self.accessor.set_sequence_indices(list(iter(loader.sampler)))
+            loader.dataset.set_accessor(self.accessor)
+            logger.info("Starting split %s" % data_type.name)
+
+            training = (mode == Mode.TRAIN) and (data_type == Split.TRAIN)
+            self.model.train(training)
+            self.criterion.train(training)
+
+            timer = EpochTimer()
+            epoch_start = time.time()
+            dataset = [d for d in problem.datasets if d.data_type == data_type][0]
+            sampler_state = SamplerState(
+                problem, len(loader.sampler), len(dataset), self.device,
+                max(self.run_opts.numVisualizedSamples, MODEL_CONVERSION_TEST_SAMPLE_CT))
+            n_batches = len(loader)
+            log = LossLog(n_tasks, n_batches, self.device)
+            checked = 0
+            batch_start = time.time()
+
+            with StepWatchdog(self.run_opts.minibatchTimeoutMs) as dog:
+                for minibatch_idx, (data, target, raw_meta) in enumerate(loader):
+                    dog.kick()
+                    data = [t.to(self.device, non_blocking=True) for t in data]
+                    target = [tuple(t.to(self.device, non_blocking=True) for t in head)
+                              for head in target]
+                    self.criterion.set_step_sink(log.row(minibatch_idx), log.nan_flag)
+                    self.criterion._sink_written = False
+                    output, total_loss, sub_loss, grad_norms = self._pass_one_minibatch(
+                        minibatch_idx, data_type, data, target)
+                    self._finish_loss_row(log, minibatch_idx, total_loss, sub_loss)
+
+                    if grad_norms is not None:
+                        contribution_count += 1
+                        for i in range(n_tasks):
+                            avg_grad_contributions[i] += (
+                                grad_norms[i] - avg_grad_contributions[i]) / contribution_count
+
+                    # lagged NaN guard: inspect rows the device has certainly finished
+                    while checked <= minibatch_idx - NAN_CHECK_LAG:
+                        log.wait(checked)
+                        self._raise_if_nan(log, checked, data_type)
+                        checked += 1
+
+                    with torch.no_grad():
+                        if minibatch_idx % amort == 0:
+                            sampler_state.compute_metrics()
+                        sampler_state.append_sample(raw_meta, data, outputs=output, targets=target)
+                        if log_freq > 0 and minibatch_idx % log_freq == 0:
+                            self._summarize_times(dataset.data_type, timer)
+                            log.wait(minibatch_idx)
+                            row = log.row(minibatch_idx).tolist()
+                            losses = dict(zip(names, row[1:]))
+                            losses["total_loss"] = row[0]
+                            logger.info("{}: {}".format(minibatch_idx, json.dumps(losses)))
+                    timer.batch.update(time.time() - batch_start)
+                    batch_start = time.time()
+
+                if self.device.type == "cuda":
+                    torch.cuda.current_stream().synchronize()
+                while checked < n_batches:
+                    self._raise_if_nan(log, checked, data_type)
+                    checked += 1
+                sampler_state.compute_metrics()
+            timer.epoch.update(time.time() - epoch_start)
+
+            per_step = log.rows[:n_batches].numpy()
+            split_loss = {name: per_step[:, 1 + i].astype(np.float64).tolist()
+                          for i, name in enumerate(names)}
+            self.last_loss_log = {"split": data_type, "rows": per_step.copy()}
+            epoch_stats[data_type] = self._epoch_summary(
+                problem, sampler_state, dataset, split_loss, timer, mode)
+
+        if self.run_opts.debugGrad:
+            logger.info("Task grad contributions: " + ", ".join(
+                "%s: %f" % (n, c) for n, c in zip(names, avg_grad_contributions)))
+        return epoch_stats
+
+    def _finish_loss_row(self, log: LossLog, step: int, total_loss, sub_loss) -> None:
+        """Make sure row ``step`` of the log gets written, then fence it with an event.
+
+        The criteria of this package write the row themselves (the fused kernel does it from
+        inside the forward launch).  A user subclass of ``BaseParallelCriterion`` that does not
+        gets the same row from one small async device-to-host copy."""
+        if not getattr(self.criterion, "_sink_written", False):
+            with torch.no_grad():
+                row = torch.stack([total_loss.detach().float()]
+                                  + [v.detach().float() for v in sub_loss.values()])
+                log.row(step).copy_(row, non_blocking=True)
+        log.mark(step)
+
+    def _raise_if_nan(self, log: LossLog, step: int, data_type: Split) -> None:
+        if np.isnan(log.rows[step % log.capacity, 0].item()):
+            raise FloatingPointError(
+                "Losses become NaN for dataset {} at iteration {} minibatch {}!".format(
+                    data_type.value, self.cur_epoch, step))
+
+    # ------------------------------------------------------------------------------------------
+    # one minibatch
+    # ------------------------------------------------------------------------------------------
+    def _cast_inputs(self, data: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        if self.precision != Precision.BF16:
+            return list(data)
+        out = []
+        for t in data:
+            if t.is_cuda and t.dtype == torch.float32:
+                lp = torch.empty_like(t, dtype=torch.bfloat16)
+                _native.cast_scale(t.contiguous(), lp, 1.0)
+                out.append(lp)
+            else:
+                out.append(t)
+        return out
+
+    def _pass_one_minibatch(self, minibatch_idx: int, data_type: Split,
+                            data: Sequence[torch.Tensor],
+                            target: Sequence[Tuple[torch.Tensor, ...]]):
+        training = self.model.training
+        debug_grad = (self.run_opts.debugGrad and isinstance(self.model, MultiTaskModel)
+                      and minibatch_idx % 10 == 0)
+        needs_graph = training or debug_grad or isinstance(self.criterion, GradNormWeightedCriterion)
+
+        if self.buffers is not None:
+            self.buffers.sync()
+        with torch.set_grad_enabled(needs_graph):
+            output = self.model(self._cast_inputs(data))
+            final_shared_params = None
+            if debug_grad or isinstance(self.criterion, GradNormWeightedCriterion):
+                final_shared_params = self.model.final_shared_params(output)
+                if isinstance(self.criterion, GradNormWeightedCriterion):
+                    self.criterion.set_shared_params(final_shared_params)
+            total_loss, sub_loss = self.criterion(output, target)
+
+        grad_norms: Optional[List[float]] = None
+        if training:
+            if debug_grad:
+                grad_norms = [torch.autograd.grad(loss, final_shared_params, retain_graph=True)[0]
+                              .norm().item() for loss in sub_loss.values()]
+            self.pipeline.begin_step()
+            total_loss.backward()
+            self.pipeline.finish_step()
+        return output, total_loss, sub_loss, grad_norms
+
+    # ------------------------------------------------------------------------------------------
+    # summaries
+    # ------------------------------------------------------------------------------------------
+    def _refine_sample_set(self, problem: Problem, samples: List[SingleSample]):
+        assert len(samples) > 0, "Can't refine an empty sample set"
+        first = samples[0]
+        target = [stack_recursive([tuple(t.detach().cpu() for t in s.target[i]) for s in samples])
+                  for i in range(len(first.target))]
+        raw_meta = {}
+        for key in first.meta:
+            vals = [s.meta[key] for s in samples]
+            raw_meta[key] = torch.stack(vals) if torch.is_tensor(vals[0]) else vals
+        meta = problem.refine_batch_meta(raw_meta)
+        output = [torch.stack([s.output[i] for s in samples]).cpu() for i in range(len(first.output))]
+        data = [torch.stack([s.data[i] for s in samples]).cpu() for i in range(len(first.data))]
+        metric = {key: np.array([s.metric[key] for s in samples]) for key in first.metric}
+        return data, target, meta, output, metric
+
+    @staticmethod
+    def _serialize_sample_summaries(summaries: Sequence[SampleSummary]
+                                    ) -> List[SerializableSampleSummary]:
+        return [SerializableSampleSummary(image=s.image, text=s.text,
+                                          plot=json.dumps(s.plot) if s.plot else None,
+                                          source=s.source) for s in summaries]
+
+    def _summarize_times(self, split: Split, timer: EpochTimer) -> None:
+        logger.info("<{}>\tEpoch: {}\tAvg Batch Time: {:.3f}\tEpoch Time: {: .3f}".format(
+            split.value.upper(), self.cur_epoch, timer.batch.avg, timer.epoch.sum))
+
+    def _epoch_summary(self, problem: Problem, sampler: SamplerState, dataset: MultifieldDataset,
+                       split_loss: Dict[str, List[float]], timer: EpochTimer, mode: Mode
+                       ) -> FractionalEpochSplitPerformanceSummary:
+        tag = dataset.data_type.value.upper()
+        self._summarize_times(dataset.data_type, timer)
+        logger.info("<{}>\tEpoch: {}\tLearning rate: {}\t".format(
+            tag, self.cur_epoch, self.optimizer.param_groups[0]["lr"]))
+        # unweighted mean over minibatches, as the reference (solver_worker.py:681)
+        epoch_split_loss = {k: float(np.mean(v)) if len(v) else float("nan")
+                            for k, v in split_loss.items()}
+        logger.info("<{}>\tEpoch: {}\t{}".format(
+            tag, self.cur_epoch, "".join("{}: {:.3f}\t".format(k, v) for k, v in epoch_split_loss.items())))
+        epoch_data_metric = problem.summarize_epoch_metrics(sampler.data_metric)
+        logger.info("<{}>\tEpoch: {}\t{}".format(
+            tag, self.cur_epoch, "".join("{}: {:.3f}\t".format(k, v) for k, v in epoch_data_metric.items())))
+
+        summary = FractionalEpochSplitPerformanceSummary(
+            nSamples=sampler.n_samples, losses=epoch_split_loss, metrics=epoch_data_metric,
+            samples=[], worstSamples=[],
+            testIO=sampler.random_samples[:MODEL_CONVERSION_TEST_SAMPLE_CT])
+        if self.run_opts.numVisualizedSamples == 0:
+            return summary
+        picked, worst = [], []
+        if sampler.random_samples:
+            picked = problem.summarize_epoch_samples(
+                *self._refine_sample_set(problem, sampler.random_samples))
+        if sampler.worst_samples:
+            worst = problem.summarize_epoch_samples(
+                *self._refine_sample_set(problem, sampler.worst_samples))
+        return summary._replace(samples=self._serialize_sample_summaries(picked),
+                                worstSamples=self._serialize_sample_summaries(worst))
+
+    def _get_worker_performance_summary(
+            self, epoch_stats: Dict[Split, FractionalEpochSplitPerformanceSummary]
+    ) -> FractionalPerformanceSummary:
+        """Model + optimizer state as device-agnostic bytes (reference solver_worker.py:733-761).
+
+        Only the rank whose state the parent will use serialises (``serialize_state``); the
+        exported module is a plain fp32 module: arena views are swapped for private copies of
+        the master weights for the duration of the pickle."""
+        model_bytes = b""
+        optim_bytes = b""
+        if self._serialize_state and self._state_wanted:
+            was_training = self.model.training
+            self.model.eval()
+            with self.arena.exported(cpu=True):
+                with io.BytesIO() as buf:
+                    torch.save(self.model, buf)
+                    model_bytes = buf.getvalue()
+            with io.BytesIO() as buf:
+                state = self.optimizer.state_dict()
+                for entry in state["state"].values():
+                    for k, v in entry.items():
+                        if torch.is_tensor(v):
+                            entry[k] = v.cpu()
+                torch.save(state, buf)
+                optim_bytes = buf.getvalue()
+            self.model.train(was_training)
+        return FractionalPerformanceSummary(epoch=self.cur_epoch, modelBuffer=model_bytes,
+                                            optimizerStateBuffer=optim_bytes,
+                                            performance=epoch_stats)
+
+    # ------------------------------------------------------------------------------------------
+    # entry points
+    # ------------------------------------------------------------------------------------------
+    def train(self, problem: Problem, startEpoch: int, nEpochs: int, batchSize: int,
+              scheduler) -> Iterator[FractionalPerformanceSummary]:
+        self.cur_epoch = startEpoch
+        assert Split.TRAIN in [d.data_type for d in problem.datasets], \
+            "training dataset should be included"
+        logger.info("Model layers")
+        logger.info(str(self.model.modules))
+        loaders = self._get_loaders(problem, batchSize=batchSize)
+        while self.cur_epoch < nEpochs:
+            self.cur_epoch += 1
+            logger.info("Starting epoch %d" % self.cur_epoch)
+            epoch_stats = self._pass_one_epoch(problem, loaders, Mode.TRAIN)
+            logger.info("Finished epoch %d" % self.cur_epoch)
+            scheduler.step()                      # once per epoch
+            self._state_wanted = (self.cur_epoch % self.save_every == 0
+                                  or self.cur_epoch == nEpochs)
+            yield self._get_worker_performance_summary(epoch_stats)
+
+    def eval(self, problem: Problem, batchSize: int) -> Iterator[FractionalPerformanceSummary]:
+        logger.info("Model layers:")
+        logger.info(str(self.model.modules))
+        loaders = self._get_loaders(problem, batchSize=batchSize)
+        epoch_stats = self._pass_one_epoch(problem, loaders, Mode.EVAL)
+        self._state_wanted = False                # the parent writes no files in EVAL mode
+        yield self._get_worker_performance_summary(epoch_stats)
+
+    def _get_loaders(self, problem: Problem, batchSize: int
+                     ) -> Dict[Split, torch.utils.data.DataLoader]:
+        loaders = {}
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+        for dataset in problem.datasets:
+            sampler = None
+            if dist_on:
+                sampler = ScaffoldSampler(dataset, shuffle_type=self.run_opts.shuffleType,
+                                          node_idx=self._node_idx, node_count=self._node_count)
+            split = dataset.data_type
+            if self.run_opts.maxEpochImages > 0:
+                logger.info("Using %d images per epoch." % self.run_opts.maxEpochImages)
+                dataset = SubsetMultifieldDataset(dataset, range(self.run_opts.maxEpochImages))
+            loaders[split] = torch.utils.data.DataLoader(
+                dataset, batch_size=batchSize, shuffle=sampler is None,
+                num_workers=self.run_opts.numThreads,
+                pin_memory=self.device.type == "cuda", sampler=sampler)
+        return loaders

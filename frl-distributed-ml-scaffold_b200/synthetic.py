@@ -1,0 +1,241 @@
+"""Synthetic multitask Problems used by the parity tests and the benchmark.
+
+The reference ships no concrete ``Problem``, so the configurations BASELINE.json
+names are defined here, written purely against the plugin API.  Every builder takes the API
+namespace as an argument: pass ``frl_b200`` to run on this package, or the reference imported
+as ``frldistml.scaffold`` (oracle only) to run the very same Problem on the reference Solver.
+
+* ``make_toy_problem``  — config 1: 64-d input, 2x128 trunk, MSE head (w=0.5) + CE head (w=2).
+* ``make_mlp_problem``  — configs 2/3: 4096-d input, 3x4096 trunk, CE head (1000) + MSE head (64).
+"""
+import importlib
+from types import SimpleNamespace
+from typing import Any, Dict, List, NamedTuple, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+def api_namespace(pkg_name: str) -> SimpleNamespace:
+    """Collect the plugin-API names from a package laid out like the reference."""
+    mod = lambda n: importlib.import_module(f"{pkg_name}.{n}")     # noqa: E731
+    types, problem, mt = mod("types"), mod("problem"), mod("multitask_problem")
+    return SimpleNamespace(
+        name=pkg_name, types=types, Split=types.Split, RunOpts=types.RunOpts,
+        OptimOpts=types.OptimOpts, OptAlgorithm=types.OptAlgorithm, Mode=types.Mode,
+        SampleSummary=types.SampleSummary,
+        Ordering=problem.Ordering, Problem=problem.Problem,
+        MultiTaskProblem=mt.MultiTaskProblem, MultiTaskTransform=mt.MultiTaskTransform,
+        Task=mod("task").Task, criteria=mod("criteria"), model=mod("model"),
+        MultifieldDataset=mod("storage_layers.dataset").MultifieldDataset)
+
+
+class NoTransformState(NamedTuple):
+    pass
+
+
+class IndexMeta(NamedTuple):
+    index: Any = None
+
+
+class NoMeta(NamedTuple):
+    pass
+
+
+class BatchMeta(NamedTuple):
+    index: Any = None
+
+
+def _array_dataset_class(ns):
+    class ArrayDataset(ns.MultifieldDataset):
+        """In-memory dataset: one ndarray per field, first axis = sample."""
+
+        def __init__(self, split, fields: Dict[str, np.ndarray], transform) -> None:
+            self.data_type = split
+            self._fields = fields
+            self._transform = transform
+            self._n = len(next(iter(fields.values())))
+            self.served: List[int] = []          # access order, for the index-parity tests
+
+        def __len__(self) -> int:
+            return self._n
+
+        def set_accessor(self, accessor) -> None:
+            pass
+
+        def get_raw_item(self, idx: int) -> Dict[str, np.ndarray]:
+            item = {k: np.asarray(v[idx]) for k, v in self._fields.items()}
+            item["index"] = np.asarray(idx, dtype=np.int64)
+            return item
+
+        def __getitem__(self, idx: int):
+            self.served.append(int(idx))
+            return self._transform(self.get_raw_item(idx), self.data_type)
+
+    return ArrayDataset
+
+
+def _task_classes(ns):
+    class RegressionTask(ns.Task):
+        def __init__(self, in_dim: int, out_dim: int, weight: float, field: str = "y_reg",
+                     name: str = "reg") -> None:
+            self._in, self._out, self._w, self._field, self.name = in_dim, out_dim, weight, field, name
+
+        @property
+        def network_head(self) -> nn.Module:
+            return nn.Linear(self._in, self._out)
+
+        @property
+        def criterion(self):
+            return nn.MSELoss()
+
+        @property
+        def criterion_weight(self) -> float:
+            return self._w
+
+        def get_target(self, tensors, transform):
+            return (tensors[self._field],), IndexMeta(index=tensors["index"])
+
+        def compute_batch_metrics(self, meta, target, output):
+            err = (output.float() - target[0].float()) ** 2
+            return {self.name + "_MSE": err.reshape(len(err), -1).mean(1).cpu().numpy()}
+
+        @property
+        def rankable_metrics(self):
+            return {(self.name + "_MSE", ns.Ordering.DESC)}
+
+        def summarize_epoch_metrics(self, batch_metrics):
+            return {self.name + "_MSE": float(np.mean(batch_metrics[self.name + "_MSE"]))}
+
+        def summarize_epoch_samples(self, data, target, meta, output, metric):
+            return [ns.SampleSummary(text="%s: %d samples" % (self.name, len(output)))]
+
+    class ClassificationTask(ns.Task):
+        def __init__(self, in_dim: int, n_classes: int, weight: float, field: str = "y_cls",
+                     name: str = "cls") -> None:
+            self._in, self._out, self._w, self._field, self.name = in_dim, n_classes, weight, field, name
+
+        @property
+        def network_head(self) -> nn.Module:
+            return nn.Linear(self._in, self._out)
+
+        @property
+        def criterion(self):
+            return nn.CrossEntropyLoss()
+
+        @property
+        def criterion_weight(self) -> float:
+            return self._w
+
+        def get_target(self, tensors, transform):
+            return (tensors[self._field],), NoMeta()
+
+        def compute_batch_metrics(self, meta, target, output):
+            wrong = (output.argmax(1) != target[0]).float()
+            return {self.name + "_err": wrong.cpu().numpy()}
+
+        @property
+        def rankable_metrics(self):
+            return {(self.name + "_err", ns.Ordering.DESC)}
+
+        def summarize_epoch_metrics(self, batch_metrics):
+            return {self.name + "_err": float(np.mean(batch_metrics[self.name + "_err"]))}
+
+        def summarize_epoch_samples(self, data, target, meta, output, metric):
+            return []
+
+    return RegressionTask, ClassificationTask
+
+
+def _problem_class(ns):
+    class CenteringTransform(ns.MultiTaskTransform):
+        """x -> (x - shift) * scale, the whole 'online preprocessing' of the synthetic configs."""
+
+        def __init__(self, tasks, shift: float, scale: float) -> None:
+            super().__init__(tasks, IndexMeta)
+            self.shift, self.scale = shift, scale
+
+        def transform_source_data(self, tensors, split):
+            return [(tensors["x"] - self.shift) * self.scale], NoTransformState()
+
+    class SyntheticMultiTaskProblem(ns.MultiTaskProblem):
+        BatchMetaType = BatchMeta
+
+        def __init__(self, tasks, trunk_dims: Sequence[int], datasets_fields, save_dir: str,
+                     shift: float, scale: float, criterion_kind: str = "parallel") -> None:
+            self._tasks = tasks
+            self._trunk_dims = list(trunk_dims)
+            self._save_dir = save_dir
+            self._criterion_kind = criterion_kind
+            self.transform = CenteringTransform(tasks, shift, scale)
+            ds_cls = _array_dataset_class(ns)
+            self._datasets = [ds_cls(split, fields, self.transform)
+                              for split, fields in datasets_fields]
+
+        @property
+        def datasets(self):
+            return self._datasets
+
+        @property
+        def save_dir(self) -> str:
+            return self._save_dir
+
+        @property
+        def anno_param(self):
+            return None
+
+        def get_model_base(self) -> nn.Module:
+            layers: List[nn.Module] = [ns.model.ListSelect(sel_index=0, num_elements=1)]
+            for d_in, d_out in zip(self._trunk_dims[:-1], self._trunk_dims[1:]):
+                layers += [nn.Linear(d_in, d_out), nn.ReLU()]
+            return nn.Sequential(*layers)
+
+        def get_criterion(self):
+            mods = [t.criterion for t in self._tasks]
+            names = [t.name for t in self._tasks]
+            weights = [t.criterion_weight for t in self._tasks]
+            c = ns.criteria
+            if self._criterion_kind == "parallel":
+                return c.ParallelCriterion(mods, weights, names)
+            if self._criterion_kind == "uncertainty":
+                LT = ns.types.LossType
+                kinds = [LT.MSE if isinstance(m, nn.MSELoss) else LT.CrossEntropy for m in mods]
+                return c.UncertaintyWeightedCriterion(mods, kinds, names, weights)
+            if self._criterion_kind == "gradnorm":
+                return c.GradNormWeightedCriterion(mods, names, alpha=1.5, base_weights=weights)
+            raise ValueError(self._criterion_kind)
+
+    return SyntheticMultiTaskProblem
+
+
+def synthetic_fields(n: int, in_dim: int, reg_dim: int, n_classes: int, seed: int,
+                     uniform_x: bool) -> Dict[str, np.ndarray]:
+    rs = np.random.RandomState(seed)
+    x = rs.rand(n, in_dim) if uniform_x else rs.randn(n, in_dim)
+    return {"x": x.astype(np.float32),
+            "y_reg": rs.randn(n, reg_dim).astype(np.float32),
+            "y_cls": rs.randint(0, n_classes, size=n).astype(np.int64)}
+
+
+def make_toy_problem(ns, save_dir: str, n_train: int = 512, n_test: int = 128,
+                     criterion_kind: str = "parallel"):
+    """Config 1: trunk 64->128->128, reg head 128->4 (w 0.5), cls head 128->10 (w 2)."""
+    Reg, Cls = _task_classes(ns)
+    tasks = [Reg(128, 4, 0.5), Cls(128, 10, 2.0)]
+    fields = [(ns.Split.TRAIN, synthetic_fields(n_train, 64, 4, 10, 0, True)),
+              (ns.Split.TEST, synthetic_fields(n_test, 64, 4, 10, 1, True))]
+    return _problem_class(ns)(tasks, [64, 128, 128], fields, save_dir, shift=0.5, scale=2.0,
+                              criterion_kind=criterion_kind)
+
+
+def make_mlp_problem(ns, save_dir: str, n_train: int = 8192, n_test: int = 0, width: int = 4096,
+                     n_classes: int = 1000, reg_dim: int = 64, depth: int = 3):
+    """Configs 2/3: trunk depth x [Linear(width,width)+ReLU], CE head width->1000 (w 1), MSE
+    head width->64 (w 1); x ~ N(0,1)."""
+    Reg, Cls = _task_classes(ns)
+    tasks = [Cls(width, n_classes, 1.0), Reg(width, reg_dim, 1.0)]
+    fields = [(ns.Split.TRAIN, synthetic_fields(n_train, width, reg_dim, n_classes, 0, False))]
+    if n_test:
+        fields.append((ns.Split.TEST, synthetic_fields(n_test, width, reg_dim, n_classes, 1, False)))
+    return _problem_class(ns)(tasks, [width] * (depth + 1), fields, save_dir, shift=0.0, scale=1.0)

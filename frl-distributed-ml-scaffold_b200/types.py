@@ -1,0 +1,127 @@
+"""Option records and enums of the scaffold plugin API.
+
+Mirrors the public names of the reference's ``types.py`` (reference types.py:36-127) so a
+``Problem`` written against the reference constructs the same ``RunOpts``/``OptimOpts`` here.
+Field names, order and defaults are the contract; the plotly dependency of the reference's
+``SampleSummary.plot`` is dropped (any JSON-serialisable figure dict is accepted).
+"""
+from enum import Enum
+from typing import Any, NamedTuple, Optional
+
+import numpy as np
+
+
+# --- enums (values are the strings the reference uses on the wire / in logs) ---------------
+
+class ShuffleType(Enum):
+    RANDPERM = "randperm"
+    PER_NODE_RANDPERM = "per_node_randperm"
+
+
+class Split(Enum):
+    TRAIN = "training"
+    TEST = "testing"
+    HELDOUT = "heldOut"
+
+
+class Device(Enum):
+    CPU = "cpu"
+    GPU = "cuda"
+
+
+class Mode(Enum):
+    EVAL = "eval"
+    TRAIN = "train"
+
+
+class OptAlgorithm(Enum):
+    RMSPROP = "rmsprop"
+    SGD = "sgd"
+    ADAM = "adam"
+
+
+class LossType(Enum):
+    MSE = "mse"
+    CrossEntropy = "crossentropy"
+
+
+class LRSchedulerAlgorithm(Enum):
+    DropEpochs = "drop"
+    WarmupMultiStepLR = "multistep"
+
+
+class Precision(Enum):
+    """Extension (not in the reference, which is fp32-only): arithmetic of the train step.
+
+    FP32  - parameters, gradients and optimizer state fp32 (reference parity mode, 1e-5 rel).
+    BF16  - bf16 shadow weights + bf16 gradients for forward/backward, fp32 master weights and
+            optimizer state in the arena, written by the fused update kernel (1e-2 tolerance).
+    """
+    FP32 = "fp32"
+    BF16 = "bf16"
+
+
+# --- records ---------------------------------------------------------------------------------
+
+class SampleSummary(NamedTuple):
+    image: Optional[np.ndarray] = None
+    text: Optional[str] = None
+    plot: Optional[Any] = None          # plotly Figure or a figure dict
+    source: Optional[str] = None
+
+
+class LRSchedulerOpts(NamedTuple):
+    algo: LRSchedulerAlgorithm = LRSchedulerAlgorithm.DropEpochs
+
+
+class OptimOpts(NamedTuple):
+    # reference types.py:85-93 — weightDecay is L2-coupled and applies to every parameter.
+    algo: OptAlgorithm
+    lr: float = 0.001
+    lr_scheduler: LRSchedulerOpts = LRSchedulerOpts()
+    weightDecay: float = 0.00001
+    momentum: float = 0.9
+    epsilon: float = 1e-8
+    amsgrad: bool = False
+    gradientClip: float = 0.0
+
+
+class RunOpts(NamedTuple):
+    # reference types.py:102-121
+    optim: OptimOpts
+    batchSize: int
+    cpuonly: bool = False
+    nEpochs: int = 75
+    maxEpochImages: int = 0             # >0: cap on samples per epoch
+    numThreads: int = 4                 # DataLoader workers
+    numIOThreads: int = 5
+    metricAmortizationSchedule: int = 10
+    initialModelPath: Optional[str] = None
+    mode: Mode = Mode.TRAIN
+    numVisualizedSamples: int = 36
+    singleThreaded: bool = False
+    outputTTL: int = 0
+    lossLoggingFreq: int = 0            # log the loss every n minibatches, 0 = never
+    debugGrad: bool = False
+    shuffleType: ShuffleType = ShuffleType.RANDPERM
+    minibatchTimeoutMs: int = 1000 * 60 * 60
+
+
+def _fill_namedtuple(cls, args, kwargs):
+    merged = dict(cls._field_defaults)
+    free = [name for name in cls.__annotations__ if name not in kwargs]
+    merged.update(zip(free, args))
+    merged.update(kwargs)
+    return merged
+
+
+class OptimOptsBase(OptimOpts):
+    """Subclassable variant: positional args fill the fields not given by keyword."""
+
+    def __new__(cls, *args, **kwargs):
+        return super().__new__(cls, **_fill_namedtuple(cls, args, kwargs))
+
+
+class RunOptsBase(RunOpts):
+    def __new__(cls, *args, **kwargs):
+        return super().__new__(cls, **_fill_namedtuple(cls, args, kwargs))

@@ -1,0 +1,155 @@
+/*
+ * frl_b200.h — C ABI of the B200 (sm_100a) data-parallel training-step kernels.
+ *
+ * The reference (facebookresearch/FRL-Distributed-ML-Scaffold) has no native boundary of its
+ * own: its step arithmetic runs inside PyTorch.  Each entry point below replaces the PyTorch
+ * call the reference makes at the cited line; the reference-side binding is the ctypes stub in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (the library never allocates or
+ *     frees caller-visible memory) unless the parameter name ends in `_host`;
+ *     `*_mapped` pointers may be pinned, device-mapped host memory;
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     immediately; nothing synchronises;
+ *   - return value: 0 = ok, negative = argument error (FRL_E_*), positive = cudaError_t of
+ *     the launch; `frl_last_error()` gives a thread-local message;
+ *   - no exceptions, no longjmp, no global mutable state except the launch counter.
+ *   - dtype codes: FRL_F32 = 0, FRL_BF16 = 1, FRL_U8 = 2, FRL_I64 = 3.
+ */
+#ifndef FRL_B200_H
+#define FRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRL_ABI_VERSION 1
+
+enum { FRL_F32 = 0, FRL_BF16 = 1, FRL_U8 = 2, FRL_I64 = 3 };
+enum { FRL_E_ARG = -1, FRL_E_ALIGN = -2, FRL_E_DTYPE = -3, FRL_E_TOO_MANY = -4 };
+
+int          frl_abi_version(void);
+const char*  frl_last_error(void);
+/* number of kernels this library has launched since load / since the last reset */
+uint64_t     frl_launch_count(void);
+void         frl_launch_count_reset(void);
+/* SM count and sm arch (major*10+minor) of the current device; <0 on error */
+int          frl_device_sm_count(void);
+int          frl_device_arch(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K2 — fused optimizer update over a flat bucket of the parameter arena.
+ * Replaces torch.optim.{SGD,Adam,RMSprop}.step() (reference solver.py:162-188, called at
+ * solver_worker.py:592) AND the DDP reducer's scale / copy-out passes (reference
+ * solver.py:287-289): the reduced gradient is read once, straight from the bucket.
+ *
+ *   p        fp32 master weights [n]           (read + written)
+ *   g        gradient bucket [n], dtype g_dtype (FRL_F32 or FRL_BF16), read once
+ *   p_lp     optional bf16 shadow weights [n] (written), NULL when the model runs in fp32
+ *   grad_scale      host scalar multiplied into g (1/world_size for the DDP mean)
+ *   grad_scale_dev  optional device scalar multiplied in as well (clip coefficient written
+ *                   by frl_grad_sumsq_clip), NULL = 1
+ * All arrays must be 16-byte aligned; n is arbitrary (scalar tail).
+ * Update rules are torch 2.11's (L2-coupled weight decay: g += wd * p first).
+ * ---------------------------------------------------------------------------------------- */
+
+/* SGD: buf = first_step ? g : mu*buf + (1-dampening)*g ; p -= lr*buf.   mu == 0: buf may be NULL. */
+int frl_sgd_momentum(float* p, const void* g, float* buf, void* p_lp, int64_t n,
+                     float lr, float mu, float dampening, float wd,
+                     float grad_scale, const float* grad_scale_dev,
+                     int first_step, int g_dtype, void* stream);
+
+/* Adam (coupled L2, optional amsgrad when vmax != NULL).  `step` is the 1-based step count
+ * used for the bias corrections (computed in double on the host side of the call). */
+int frl_adam(float* p, const void* g, float* m, float* v, float* vmax, void* p_lp, int64_t n,
+             float lr, float beta1, float beta2, float eps, float wd, int64_t step,
+             float grad_scale, const float* grad_scale_dev, int g_dtype, void* stream);
+
+/* RMSprop (not centered): sq = alpha*sq + (1-alpha)*g^2 ; avg = sqrt(sq)+eps ;
+ * mu > 0: buf = mu*buf + g/avg ; p -= lr*buf     else: p -= lr*g/avg  (buf may be NULL). */
+int frl_rmsprop(float* p, const void* g, float* sq, float* buf, void* p_lp, int64_t n,
+                float lr, float alpha, float eps, float wd, float mu,
+                float grad_scale, const float* grad_scale_dev, int g_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 — global gradient norm for clipping.
+ * Replaces torch.nn.utils.clip_grad_norm_ (reference solver_worker.py:588-591): one pass
+ * over the model-parameter range of the gradient arena.
+ *   out[0] = sum(g^2) * pre_scale^2,  out[1] = sqrt(out[0]),
+ *   out[2] = min(1, max_norm / (out[1] + 1e-6))   (the coefficient K2 reads)
+ * scratch: >= frl_reduce_scratch_floats() floats + 1 uint32 ticket, zero-initialised once.
+ * Deterministic: fixed-order two-stage reduction.
+ * ---------------------------------------------------------------------------------------- */
+int64_t frl_reduce_scratch_bytes(void);
+int frl_grad_sumsq_clip(const void* g, int64_t n, int g_dtype, float pre_scale, float max_norm,
+                        float* out3, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4 — fused multitask criterion.
+ * Replaces ParallelCriterion.compute_split_loss/forward (reference criteria.py:42-61), the
+ * nn.MSELoss / nn.CrossEntropyLoss kernels underneath, MaskedLoss's gather
+ * (criteria.py:267-287) and the isnan()/item() syncs of the loop (solver_worker.py:486-487,
+ * 569).
+ * ---------------------------------------------------------------------------------------- */
+#define FRL_MAX_TASKS 8
+enum { FRL_LOSS_MSE = 0, FRL_LOSS_CE = 1 };
+
+typedef struct frl_task_desc {
+    int32_t     kind;         /* FRL_LOSS_MSE | FRL_LOSS_CE */
+    int32_t     out_dtype;    /* FRL_F32 | FRL_BF16 : dtype of `out` (and of `dout`) */
+    int32_t     tgt_dtype;    /* MSE: FRL_F32 | FRL_BF16 ; CE: FRL_I64 */
+    int32_t     ignore_index; /* CE only (torch default -100) */
+    const void* out;          /* model output  [rows, cols] row-major contiguous */
+    const void* tgt;          /* MSE: [rows, cols] ; CE: int64 class index [rows] */
+    const uint8_t* mask;      /* optional (MaskedLoss): nonzero = use ; numel = rows*cols/mask_inner */
+    void*       dout;         /* backward only: gradient wrt out, same shape/dtype as out */
+    int64_t     rows;
+    int64_t     cols;
+    int64_t     mask_inner;   /* elements of `out` covered by one mask entry (1 or cols ...) */
+    float       weight;       /* loss weight w_i */
+    float       _pad;
+} frl_task_desc;
+
+/* scratch bytes for T tasks (partials + ticket); zero-initialise once */
+int64_t frl_criteria_scratch_bytes(int n_tasks);
+
+/* forward: losses[0] = sum_i w_i*L_i (left-to-right), losses[1+i] = w_i*L_i.
+ *   aux[i]      = 1/count_i (0 if nothing selected) for the backward
+ *   lse[...]    = per-row log-sum-exp of every CE task, rows concatenated in task order
+ *   sink_mapped = optional second destination of losses[0..T] (e.g. a row of a pinned loss
+ *                 log), nan_flag_mapped = optional int set to 1 when losses[0] is NaN. */
+int frl_criteria_forward(const frl_task_desc* tasks_host, int n_tasks,
+                         float* losses, float* aux, float* lse,
+                         float* sink_mapped, int32_t* nan_flag_mapped,
+                         void* scratch, void* stream);
+
+/* backward: dout_i = (gl[0] + gl[1+i]) * w_i * dL_i/dout_i, gl = gradient wrt losses[0..T]
+ * (device, fp32 [1+T]); reads aux / lse written by the forward. */
+int frl_criteria_backward(const frl_task_desc* tasks_host, int n_tasks,
+                          const float* grad_losses, const float* aux, const float* lse,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5 — device-side batch preprocessing.
+ * Batched replacement of the per-sample MultifieldTransform arithmetic (reference
+ * transform.py:25-38, multitask_problem.py:56-71): dst = (src * scale[c] + bias[c]), with
+ * c = (i / inner) % channels, converting FRL_U8|FRL_F32|FRL_BF16 -> FRL_F32|FRL_BF16.
+ * scale/bias: device fp32 [channels]; NULL scale = 1, NULL bias = 0.
+ * ---------------------------------------------------------------------------------------- */
+int frl_preproc_affine(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
+                       int64_t inner, int64_t channels, const float* scale, const float* bias,
+                       void* stream);
+
+/* dtype conversion / scaled copy used by the arena (master -> shadow refresh after a
+ * checkpoint load, gradient flatten for modules the arena cannot write into directly):
+ * dst = src * scale. */
+int frl_cast_scale(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
+                   float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRL_B200_H */
