@@ -300,6 +300,7 @@ class SolverWorker:
         self._local_rank = local_rank
         self._serialize_state = serialize_state
         self._state_wanted = True      # False for epochs whose state the parent will not save
+        self.loss_history: List[Tuple[int, Split, np.ndarray]] = []
         self.save_every = 1
         self.optimizer.zero_grad()
         if device.type == "cuda":
@@ -397,7 +398,8 @@ class SolverWorker:
             per_step = log.rows[:n_batches].numpy()
             split_loss = {name: per_step[:, 1 + i].astype(np.float64).tolist()
                           for i, name in enumerate(names)}
-            self.last_loss_log = {"split": data_type, "rows": per_step.copy()}
+            # per-step [total, sub-losses...] of every split, in the order they were run
+            self.loss_history.append((self.cur_epoch, data_type, per_step.copy()))
             epoch_stats[data_type] = self._epoch_summary(
                 problem, sampler_state, dataset, split_loss, timer, mode)
 

@@ -109,7 +109,7 @@ class RunOpts(NamedTuple):
 
 def _fill_namedtuple(cls, args, kwargs):
     merged = dict(cls._field_defaults)
-    free = [name for name in cls.__annotations__ if name not in kwargs]
+    free = [name for name in cls._fields if name not in kwargs]
     merged.update(zip(free, args))
     merged.update(kwargs)
     return merged

@@ -1,0 +1,201 @@
+"""Host-side logic of the arena, the fused optimizers and the bucket pipeline on CPU tensors.
+The kernel entry points are replaced by ``oracle.optim_np.KernelDouble`` (a test double with the
+same call signatures) — this exercises layout, bucketing, state (de)serialisation and the
+multi-rank protocol, not the kernels."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+import frl_b200  # noqa: F401
+from frl_b200 import fused_optim, grad_sync
+from frl_b200.arena import ALIGN_ELEMS, ParamArena
+from frl_b200.types import OptAlgorithm, OptimOpts, Precision
+from oracle.optim_np import KernelDouble
+
+
+@pytest.fixture()
+def double(monkeypatch):
+    d = KernelDouble()
+    monkeypatch.setattr(fused_optim, "KERNELS", d)
+    monkeypatch.setattr(grad_sync, "KERNELS", d)
+    return d
+
+
+def _net(seed=0):
+    torch.manual_seed(seed)
+    return nn.Sequential(nn.Linear(7, 5), nn.ReLU(), nn.Linear(5, 3), nn.ReLU(), nn.Linear(3, 2))
+
+
+def test_arena_layout_and_views():
+    net = _net()
+    before = [p.detach().clone() for p in net.parameters()]
+    extra = nn.Parameter(torch.tensor([0.5, -0.25]))
+    arena = ParamArena(net.parameters(), [extra], device="cpu")
+    assert arena.numel % ALIGN_ELEMS == 0 and arena.model_end % ALIGN_ELEMS == 0
+    for s in arena.slots:
+        assert s.offset % ALIGN_ELEMS == 0
+    for p, b in zip(net.parameters(), before):
+        assert torch.equal(p, b)
+        s = arena.slot_of(p)
+        assert p.data_ptr() == arena.master[s.offset:].data_ptr()     # a view, not a copy
+    assert arena.slots[-1].is_model is False and arena.slots[-1].offset == arena.model_end
+    # padding stays zero
+    used = torch.zeros(arena.numel, dtype=torch.bool)
+    for s in arena.slots:
+        used[s.offset:s.end] = True
+    assert torch.all(arena.master[~used] == 0)
+    # buckets cover the arena back to front
+    buckets = arena.buckets(cap_bytes=64)
+    assert buckets[0][1] == arena.numel and buckets[-1][0] == 0
+    assert all(a[0] == b[1] for a, b in zip(buckets[:-1], buckets[1:]))
+    with arena.exported():
+        sd = {k: v.clone() for k, v in net.state_dict().items()}
+        assert all(v.data_ptr() != arena.master.data_ptr() for v in sd.values())
+    for p in net.parameters():
+        assert p.data_ptr() >= arena.master.data_ptr()
+
+
+def test_bf16_arena_keeps_fp32_master_and_bf16_views():
+    net = _net()
+    arena = ParamArena(net.parameters(), device="cpu", precision=Precision.BF16)
+    assert arena.grad.dtype == torch.bfloat16 and arena.lp.dtype == torch.bfloat16
+    for p in net.parameters():
+        assert p.dtype == torch.bfloat16
+    assert arena.master.dtype == torch.float32
+    assert torch.equal(arena.lp.float(), arena.master.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("algo,kw", [
+    (OptAlgorithm.SGD, {}), (OptAlgorithm.ADAM, {}), (OptAlgorithm.ADAM, {"amsgrad": True}),
+    (OptAlgorithm.RMSPROP, {})])
+def test_fused_optimizer_follows_torch_optim_and_round_trips_state(double, algo, kw):
+    from oracle.ref_loop import OptimSpec, make_optimizer
+    net, ref = _net(1), _net(1)
+    opts = OptimOpts(algo=algo, lr=0.01, **kw)
+    arena = ParamArena(net.parameters(), device="cpu")
+    opt = fused_optim.create_fused_optimizer(arena, opts)
+    pipe = grad_sync.GradBucketPipeline(arena, opt)
+    ref_opt = make_optimizer(ref.parameters(), OptimSpec(algo=algo.value, lr=0.01,
+                                                         amsgrad=kw.get("amsgrad", False)))
+    x = torch.randn(16, 7)
+    for step in range(4):
+        for m, o in ((net, None), (ref, ref_opt)):
+            loss = m(x).square().mean()
+            if o is None:
+                pipe.begin_step()
+                loss.backward()
+                pipe.finish_step()
+            else:
+                o.zero_grad()
+                loss.backward()
+                o.step()
+    for a, b in zip(net.parameters(), ref.parameters()):
+        np.testing.assert_allclose(a.detach().numpy(), b.detach().numpy(), rtol=1e-5, atol=1e-7)
+    # state dict is torch-format and interchangeable
+    sd = opt.state_dict()
+    ref_sd = ref_opt.state_dict()
+    assert sorted(sd["state"].keys()) == sorted(ref_sd["state"].keys())
+    for k, entry in ref_sd["state"].items():
+        for name, val in entry.items():
+            if torch.is_tensor(val) and val.dim() > 0:
+                np.testing.assert_allclose(sd["state"][k][name].numpy(), val.numpy(),
+                                           rtol=1e-4, atol=1e-6)
+    # load the torch optimizer's state into a fresh fused optimizer and keep stepping in sync
+    net2 = _net(1)
+    with torch.no_grad():
+        for a, b in zip(net2.parameters(), ref.parameters()):
+            a.copy_(b)
+    arena2 = ParamArena(net2.parameters(), device="cpu")
+    opt2 = fused_optim.create_fused_optimizer(arena2, opts)
+    opt2.load_state_dict(ref_sd)
+    pipe2 = grad_sync.GradBucketPipeline(arena2, opt2)
+    pipe2.begin_step(); net2(x).square().mean().backward(); pipe2.finish_step()
+    ref_opt.zero_grad(); ref(x).square().mean().backward(); ref_opt.step()
+    for a, b in zip(net2.parameters(), ref.parameters()):
+        np.testing.assert_allclose(a.detach().numpy(), b.detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_clip_applies_to_model_parameters_only(double):
+    net, ref = _net(2), _net(2)
+    extra, ref_extra = nn.Parameter(torch.tensor([1.0])), nn.Parameter(torch.tensor([1.0]))
+    arena = ParamArena(net.parameters(), [extra], device="cpu")
+    opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm.SGD, lr=0.1))
+    pipe = grad_sync.GradBucketPipeline(arena, opt, clip_norm=0.05)
+    ref_opt = torch.optim.SGD(list(ref.parameters()) + [ref_extra], lr=0.1, momentum=0.9,
+                              weight_decay=1e-5)
+    x = torch.randn(8, 7)
+    pipe.begin_step(); (net(x).square().mean() * extra.sum() * 3).backward(); pipe.finish_step()
+    (ref(x).square().mean() * ref_extra.sum() * 3).backward()
+    torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05)
+    ref_opt.step()
+    for a, b in zip(list(net.parameters()) + [extra], list(ref.parameters()) + [ref_extra]):
+        np.testing.assert_allclose(a.detach().numpy(), b.detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_unused_parameter_is_skipped_like_torch_optim(double):
+    net, ref = _net(3), _net(3)
+    arena = ParamArena(net.parameters(), device="cpu")
+    opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm.SGD, lr=0.1))
+    pipe = grad_sync.GradBucketPipeline(arena, opt)
+    ref_opt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-5)
+    x = torch.randn(8, 7)
+    pipe.begin_step(); net[0](x).square().mean().backward(); pipe.finish_step()   # only layer 0
+    ref[0](x).square().mean().backward(); ref_opt.step()
+    for a, b in zip(net.parameters(), ref.parameters()):
+        np.testing.assert_allclose(a.detach().numpy(), b.detach().numpy(), rtol=1e-6, atol=1e-8)
+
+
+# ---- world_size 2 over gloo ---------------------------------------------------------------------
+
+def _rank_main(rank, world, port, algo_value, clip, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = KernelDouble()
+    fused_optim.KERNELS = d
+    grad_sync.KERNELS = d
+    net = _net(10 + rank)                      # deliberately different: broadcast must fix it
+    arena = ParamArena(net.parameters(), device="cpu")
+    opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm(algo_value), lr=0.05))
+    pipe = grad_sync.GradBucketPipeline(arena, opt, world_size=world, clip_norm=clip,
+                                        bucket_cap_mb=0.0001, first_bucket_mb=0.00005)
+    pipe.broadcast_parameters(src=0)
+    assert len(pipe.buckets) > 1
+    g = torch.Generator().manual_seed(99)
+    for step in range(3):
+        x = torch.randn(8 * world, 7, generator=g)
+        pipe.begin_step()
+        net(x[rank::world]).square().mean().backward()
+        pipe.finish_step()
+    torch.save([p.detach().clone() for p in net.parameters()], os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("algo,clip", [("sgd", 0.0), ("adam", 0.0), ("sgd", 0.01)])
+def test_two_rank_pipeline_equals_global_batch_training(tmp_path, algo, clip):
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_rank_main, args=(world, port, algo, clip, str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(tmp_path / "r0.pt")
+    r1 = torch.load(tmp_path / "r1.pt")
+    for a, b in zip(r0, r1):
+        assert torch.equal(a, b)                               # replicas stay identical
+    # single-process oracle on the concatenated batch (mean of per-rank means == global mean)
+    from oracle.ref_loop import OptimSpec, make_optimizer
+    ref = _net(10)
+    ref_opt = make_optimizer(ref.parameters(), OptimSpec(algo=algo, lr=0.05))
+    g = torch.Generator().manual_seed(99)
+    for step in range(3):
+        x = torch.randn(8 * world, 7, generator=g)
+        ref_opt.zero_grad()
+        ref(x).square().mean().backward()
+        if clip:
+            torch.nn.utils.clip_grad_norm_(ref.parameters(), clip)
+        ref_opt.step()
+    for a, b in zip(r0, ref.parameters()):
+        np.testing.assert_allclose(a.numpy(), b.detach().numpy(), rtol=2e-5, atol=1e-7)

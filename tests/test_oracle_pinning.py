@@ -1,0 +1,153 @@
+"""The oracle (oracle/ref_loop.py, optim_np.py, criteria_np.py) against the committed golden
+vectors recorded from the live reference, against the reference itself where it is present,
+and against torch's own ops."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import criteria_np, optim_np, ref_loop
+from oracle.make_golden import BATCH, CONFIGS, SEED, run_oracle
+
+
+def _golden_rows(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_ref_loop_reproduces_reference_run(golden_dir, name):
+    g = _golden_rows(golden_dir, name)
+    trace, problem = run_oracle(name, CONFIGS[name])
+    rows = np.concatenate([trace.losses[k] for k in sorted(
+        trace.losses, key=lambda ek: (ek[0], 0 if ek[1] == "training" else 1))])
+    # bit-exact on the machine that made the fixture; other CPUs may pick different SIMD paths
+    np.testing.assert_allclose(rows, g["rows"], rtol=2e-6, atol=1e-7)
+    served = sum((trace.indices[k] for k in sorted(trace.indices) if k[1] == "training"), [])
+    assert served == list(g["served_train"])            # sample order: exact
+    n_param = len([k for k in g.files if k.startswith("param_") and k != "param_names"])
+    for i in range(n_param):
+        np.testing.assert_allclose(trace.params[i], g["param_%02d" % i], rtol=2e-5, atol=2e-7)
+    lrs = [lr for lr, e in zip(g["lr"], g["epoch"])]
+    for lr, epoch in zip(lrs, g["epoch"]):
+        assert lr == pytest.approx(trace.lrs[epoch - 1], rel=1e-12)
+
+
+def test_lr_closed_forms_match_reference_tables(golden_dir):
+    table = json.load(open(os.path.join(golden_dir, "lr_schedules.json")))
+    for key, lrs in table.items():
+        if key.startswith("kat_"):
+            continue
+        sched, n = key.split("_n")
+        got = [ref_loop.lr_at_epoch(0.1, e, int(n), sched) for e in range(1, int(n) + 1)]
+        assert got == pytest.approx(lrs, rel=1e-12)
+    # the reference's own known-answer test (tests/test_solver.py:17-34)
+    assert table["kat_resume60_adam_lr0.01_n75"] == [pytest.approx(0.001)]
+    assert ref_loop.lr_at_epoch(0.01, 61, 75, "drop") == pytest.approx(0.001)
+
+
+def test_sampler_restatement_matches_reference_lists(golden_dir):
+    table = json.load(open(os.path.join(golden_dir, "samplers.json")))
+    assert table["randperm_n10_w4_nodes1_e1"] == [[5, 0, 7], [6, 8, 4], [1, 9, 5], [2, 3, 6]]
+    for key, per_rank in table.items():
+        m = re.fullmatch(r"(\w+)_n(\d+)_w(\d+)_nodes(\d+)_e(\d+)", key)
+        kind = m.group(1)
+        n, w, nodes, e = (int(m.group(i)) for i in (2, 3, 4, 5))
+        for rank, expect in enumerate(per_rank):
+            node_size = w // nodes
+            got = ref_loop.rank_indices(n, e, rank, w, kind, node_idx=rank // node_size,
+                                        node_count=nodes)
+            assert got == expect, key
+
+
+@pytest.mark.reference
+def test_ref_loop_equals_live_reference_bitwise():
+    from oracle.make_golden import run_live_reference
+    name = "toy_sgd"
+    live = run_live_reference(name, CONFIGS[name])
+    trace, _ = run_oracle(name, CONFIGS[name])
+    rows = np.concatenate([trace.losses[k] for k in sorted(
+        trace.losses, key=lambda ek: (ek[0], 0 if ek[1] == "training" else 1))])
+    assert np.array_equal(rows, live["rows"])
+    assert np.array_equal(trace.params[0], live["param_00"])
+
+
+# ---- numpy update rules vs torch.optim (what the reference actually calls) --------------------
+
+def _torch_steps(opt_cls, kwargs, p0, grads):
+    p = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = opt_cls([p], **kwargs)
+    for g in grads:
+        p.grad = torch.from_numpy(g.copy())
+        opt.step()
+    return p.detach().numpy()
+
+
+def test_numpy_rules_match_torch_optim():
+    rs = np.random.RandomState(3)
+    p0 = rs.randn(257).astype(np.float32)
+    grads = [rs.randn(257).astype(np.float32) for _ in range(5)]
+    # SGD momentum
+    want = _torch_steps(torch.optim.SGD, dict(lr=0.01, momentum=0.9, weight_decay=1e-5), p0, grads)
+    p, buf = p0.copy(), np.zeros_like(p0)
+    for i, g in enumerate(grads):
+        p, buf = optim_np.sgd_step(p, g, buf, lr=0.01, mu=0.9, dampening=0.0, wd=1e-5,
+                                   first_step=(i == 0))
+    np.testing.assert_allclose(p, want, rtol=1e-6, atol=1e-7)
+    # Adam (+amsgrad)
+    for ams in (False, True):
+        want = _torch_steps(torch.optim.Adam, dict(lr=1e-3, weight_decay=1e-5, eps=1e-8,
+                                                   amsgrad=ams), p0, grads)
+        p, m, v = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+        vmax = np.zeros_like(p0) if ams else None
+        for i, g in enumerate(grads):
+            p, m, v, vmax = optim_np.adam_step(p, g, m, v, vmax, lr=1e-3, beta1=0.9, beta2=0.999,
+                                               eps=1e-8, wd=1e-5, step=i + 1)
+        np.testing.assert_allclose(p, want, rtol=2e-6, atol=1e-7)
+    # RMSprop with and without momentum
+    for mu in (0.9, 0.0):
+        want = _torch_steps(torch.optim.RMSprop, dict(lr=1e-3, momentum=mu, weight_decay=1e-5),
+                            p0, grads)
+        p, sq, buf = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+        for g in grads:
+            p, sq, buf = optim_np.rmsprop_step(p, g, sq, buf, lr=1e-3, alpha=0.99, eps=1e-8,
+                                               wd=1e-5, mu=mu)
+        np.testing.assert_allclose(p, want, rtol=2e-6, atol=1e-7)
+
+
+def test_numpy_criteria_match_torch_losses():
+    rs = np.random.RandomState(5)
+    out = rs.randn(33, 7).astype(np.float32)
+    tgt = rs.randn(33, 7).astype(np.float32)
+    lab = rs.randint(0, 7, size=33)
+    lab[3] = -100
+    to, tt, tl = (torch.tensor(out, requires_grad=True), torch.tensor(tgt), torch.tensor(lab))
+    l = torch.nn.functional.mse_loss(to, tt)
+    l.backward()
+    loss, grad = criteria_np.mse(out, tgt)
+    assert loss == pytest.approx(l.item(), rel=1e-6)
+    np.testing.assert_allclose(grad, to.grad.numpy(), rtol=1e-5, atol=1e-8)
+    to.grad = None
+    l = torch.nn.functional.cross_entropy(to, tl)
+    l.backward()
+    loss, grad = criteria_np.cross_entropy(out, lab)
+    assert loss == pytest.approx(l.item(), rel=1e-6)
+    np.testing.assert_allclose(grad, to.grad.numpy(), rtol=1e-5, atol=1e-8)
+    # masked variants against the reference's gather formulation
+    mask = rs.rand(33) > 0.5
+    ref = ref_loop.masked_loss(torch.nn.MSELoss(), torch.tensor(out), torch.tensor(tgt),
+                               torch.tensor(mask))
+    assert criteria_np.mse(out, tgt, mask)[0] == pytest.approx(ref.item(), rel=1e-6)
+    empty = np.zeros(33, dtype=bool)
+    ref0 = ref_loop.masked_loss(torch.nn.CrossEntropyLoss(), torch.tensor(out), torch.tensor(lab).clamp(min=0),
+                                torch.tensor(empty))
+    assert criteria_np.cross_entropy(out, lab, empty)[0] == pytest.approx(ref0.item(), rel=1e-6)
+    assert criteria_np.mse(out, tgt, empty)[0] == 0.0
+
+
+def test_bf16_round_matches_torch():
+    x = np.random.RandomState(1).randn(4097).astype(np.float32) * 3
+    want = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    assert np.array_equal(optim_np.bf16_round(x), want)
