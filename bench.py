@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Headline benchmark: samples/sec of the data-parallel training step on the synthetic 2-task
+MLP Problem (BASELINE.json configs[1] at N=1, configs[2] at N>1; batch 4096 per rank).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+    python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host CPU
+
+One JSON line on stdout (rank 0).  Everything else goes to stderr.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "samples/sec (whole box) on synthetic 2-task Problem"
+WIDTH, N_CLASSES, REG_DIM, DEPTH = 4096, 1000, 64, 3
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--algo", default="sgd", choices=["sgd", "adam", "rmsprop"])
+    ap.add_argument("--batch", type=int, default=4096, help="samples per rank per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=1024, help="CPU arm: samples per step (bounded sample)")
+    ap.add_argument("--cpu-steps", type=int, default=3, help="cpu_baseline leg: timed steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# shared: the Problem
+# --------------------------------------------------------------------------------------------------
+
+def workload_name(batch, algo):
+    return ("2-task MLP Problem: 4096-d in, 3x[Linear(4096,4096)+ReLU] trunk, heads 4096->1000 CE + "
+            "4096->64 MSE (54.70M params), batch %d/rank, %s wd=1e-5" % (
+                batch, {"sgd": "SGD momentum 0.9 lr 0.01", "adam": "Adam lr 1e-3",
+                        "rmsprop": "RMSprop momentum 0.9 lr 1e-3"}[algo]))
+
+
+def build_problem(ns, save_dir):
+    from frl_b200 import synthetic
+    return synthetic.make_mlp_problem(ns, save_dir, n_train=64, width=WIDTH, n_classes=N_CLASSES,
+                                      reg_dim=REG_DIM, depth=DEPTH)
+
+
+def run_opts_for(ns, algo, batch):
+    t = ns.types
+    lr = 0.01 if algo == "sgd" else 1e-3
+    return t.RunOpts(optim=t.OptimOpts(algo=t.OptAlgorithm(algo), lr=lr), batchSize=batch,
+                     nEpochs=1, numThreads=0, singleThreaded=True, numVisualizedSamples=0)
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle restatement) on the host cores
+# --------------------------------------------------------------------------------------------------
+
+def time_cpu_reference(algo, batch, steps, warmup):
+    """Reference `_pass_one_minibatch` (oracle/ref_loop.reference_minibatch: stock fp32 torch on
+    the CPU, torch.optim, un-fused criterion) on a bounded sample of the workload."""
+    import torch
+    import frl_b200  # noqa: F401  (only the synthetic Problem definition)
+    from frl_b200 import synthetic
+    from oracle import ref_loop
+    ns = synthetic.api_namespace("frl_b200")
+    torch.manual_seed(0)
+    problem = build_problem(ns, "/tmp/frl_b200_bench_cpu")
+    model = problem.get_model()
+    crit = problem.get_criterion()
+    mods, weights, names = list(crit.loss_modules), list(crit.loss_weights), list(crit.loss_names)
+    spec = ref_loop.OptimSpec(algo=algo, lr=0.01 if algo == "sgd" else 1e-3)
+    params = list(model.parameters())
+    opt = ref_loop.make_optimizer(params, spec)
+
+    def criterion_fn(outputs, targets):
+        return ref_loop.parallel_criterion(mods, weights, names, outputs, targets)
+
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, WIDTH, generator=g)
+    y = torch.randint(0, N_CLASSES, (batch,), generator=g)
+    r = torch.randn(batch, REG_DIM, generator=g)
+    model.train()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        ref_loop.reference_minibatch(model, criterion_fn, opt, params, 0.0, [x], [(y,), (r,)])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": batch * steps / total, "unit": "samples/s", "cores": os.cpu_count(),
+            "torch_threads": torch.get_num_threads(), "kind": "port",
+            "sample": "%d timed steps (+%d warm-up) of the same 2-task MLP at batch %d, fp32, "
+                      "oracle/ref_loop.reference_minibatch (stock torch CPU ops + torch.optim)" % (
+                          steps, warmup, batch),
+            "ms_per_step": 1e3 * total / steps, "step_p50_ms": 1e3 * statistics.median(times)}
+
+
+def main_reference(args, rank):
+    if rank != 0:
+        return
+    res = time_cpu_reference(args.algo, args.cpu_batch, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step"], "step_p50_ms": res["step_p50_ms"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.cpu_batch, args.algo),
+                       "note": "reference algorithm on the host CPU; bounded sample: batch %d "
+                               "per step instead of %d" % (args.cpu_batch, args.batch)},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:                      # noqa: BLE001
+            log("clock sampling unavailable:", e)
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:                       # noqa: BLE001
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+
+BYTES_PER_PARAM = {  # algorithmic, fp32 master + state, bf16 gradient read, bf16 shadow written
+    ("sgd", "bf16"): 2 + 4 + 4 + 4 + 4 + 2, ("sgd", "fp32"): 4 + 4 + 4 + 4 + 4,
+    ("adam", "bf16"): 2 + 4 * 3 + 4 * 3 + 2, ("adam", "fp32"): 4 * 4 + 4 * 3,
+    ("rmsprop", "bf16"): 2 + 4 * 3 + 4 * 3 + 2, ("rmsprop", "fp32"): 4 * 4 + 4 * 3}
+
+
+def main_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import frl_b200  # noqa: F401
+    from frl_b200 import _native, synthetic
+    from frl_b200.solver import Solver, SolverWorkerArgs
+    from frl_b200.solver_worker import LossLog
+    from frl_b200.types import Device, Precision
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ns = synthetic.api_namespace("frl_b200")
+    t = ns.types
+    precision = Precision(args.precision)
+    B = args.batch
+
+    torch.manual_seed(0)
+    save_dir = "/tmp/frl_b200_bench_%d" % rank
+    os.makedirs(save_dir, exist_ok=True)
+    problem = build_problem(ns, save_dir)
+    wargs = SolverWorkerArgs(run_opts=run_opts_for(ns, args.algo, B), problem=problem,
+                             save_dir=save_dir, run_device=Device.GPU, node_idx=0, node_count=1,
+                             rank=rank, local_rank=local_rank, world_size=world, group_name=None,
+                             init_method="env://", precision=precision)
+    worker, _, _ = Solver.build_worker(wargs)
+    worker.model.train()
+    worker.criterion.train()
+    arena = worker.arena
+    n_tasks = len(worker.criterion.loss_names)
+    log("rank %d: arena %d elements, grad dtype %s, buckets %d" % (
+        rank, arena.numel, arena.grad_dtype, len(worker.pipeline.buckets)))
+
+    # ---- synthetic batches (generated on the device; seed 1234 + rank) ----
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    POOL = 4
+    pool = []
+    for _ in range(POOL):
+        x = torch.randn(B, WIDTH, device=dev, generator=gen)
+        y = torch.randint(0, N_CLASSES, (B,), device=dev, generator=gen)
+        r = torch.randn(B, REG_DIM, device=dev, generator=gen)
+        pool.append(([x], [(y,), (r,)]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        tv = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        return tv.item()
+
+    W, K = args.warmup, args.steps
+    log_ring = LossLog(n_tasks, W + K + 8, dev)
+
+    def step_resident(i):
+        data, target = pool[i % POOL]
+        worker.criterion.set_step_sink(log_ring.row(i), log_ring.nan_flag)
+        worker._pass_one_minibatch(i, t.Split.TRAIN, data, target)
+
+    # ======================= leg 1: inputs resident in HBM =======================
+    for i in range(W):
+        step_resident(i)
+    barrier()
+    worker.pipeline.update_events.clear()
+    worker.pipeline.record_update_events = True
+    launches0 = _native.launch_count()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    with ClockSampler(local_rank) as clocks:
+        marks[0].record()
+        for i in range(K):
+            step_resident(W + i)
+            marks[i + 1].record()
+        barrier()
+    launches = _native.launch_count() - launches0
+    worker.pipeline.record_update_events = False
+    total_ms = marks[0].elapsed_time(marks[K])
+    step_ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(K)]
+    total_ms = max_over_ranks(total_ms)
+    value = world * B * K / (total_ms / 1e3)
+    losses = log_ring.rows[W:W + K, 0]
+    assert torch.isfinite(losses).all(), "non-finite loss in the timed region"
+
+    # roofline of the dominant kernel of OUR path: the fused update (K2), timed live by events
+    # recorded on the launching stream around every launch inside the timed region
+    upd = worker.pipeline.update_events
+    upd_ms = [e0.elapsed_time(e1) for e0, e1, _, _ in upd]
+    upd_elems = sum(hi - lo for _, _, lo, hi in upd)
+    bpp = BYTES_PER_PARAM[(args.algo, args.precision)]
+    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = bpp * upd_elems / (sum(upd_ms) / 1e3) / 1e9 if upd_ms else None
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "k2_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("%s_%s" % (args.algo, args.precision))
+    roofline = {"bound": "hbm", "kernel": "frl::update_kernel (fused grad-bucket + optimizer, K2)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "peak_source": peak_src, "bytes_per_param": bpp,
+                "elems_per_step": upd_elems // max(K, 1), "launches_per_step": len(upd) / max(K, 1),
+                "avg_launch_ms": (sum(upd_ms) / len(upd_ms)) if upd_ms else None,
+                "share_of_step": (sum(upd_ms) / K) / (total_ms / K) if upd_ms else None}
+
+    # ======================= leg 2: end to end from host buffers =======================
+    e2e = None
+    if not args.no_e2e:
+        host = []
+        for data, target in pool:
+            host.append(([d.cpu().pin_memory() for d in data],
+                         [tuple(tt.cpu().pin_memory() for tt in head) for head in target]))
+        h2d_bytes = sum(d.numel() * d.element_size() for d in host[0][0]) + sum(
+            tt.numel() * tt.element_size() for head in host[0][1] for tt in head)
+        copy_stream = torch.cuda.Stream(device=dev)
+        slots = [([torch.empty_like(d, device=dev) for d in host[0][0]],
+                  [tuple(torch.empty_like(tt, device=dev) for tt in head) for head in host[0][1]])
+                 for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        for ev in freed:
+            ev.record()
+
+        def upload(i):
+            s = i % 2
+            src = host[i % POOL]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[s])
+                for d, h in zip(slots[s][0], src[0]):
+                    d.copy_(h, non_blocking=True)
+                for dh, hh in zip(slots[s][1], src[1]):
+                    for d, h in zip(dh, hh):
+                        d.copy_(h, non_blocking=True)
+                ready[s].record()
+
+        seen = []
+
+        def step_e2e(i, base):
+            s = i % 2
+            if i == 0:
+                upload(0)
+            upload(i + 1)                       # prefetch the next batch while this one computes
+            torch.cuda.current_stream().wait_event(ready[s])
+            worker.criterion.set_step_sink(log_ring.row(base + i), log_ring.nan_flag)
+            worker._pass_one_minibatch(base + i, t.Split.TRAIN, slots[s][0], slots[s][1])
+            freed[s].record()
+            log_ring.mark(base + i)
+            if i >= 2:                          # device -> host: the loss row the kernel wrote
+                log_ring.wait(base + i - 2)
+                seen.append(float(log_ring.rows[(base + i - 2) % log_ring.capacity, 0]))
+
+        # reuse the ring: e2e steps overwrite rows from 0
+        for i in range(W):
+            step_e2e(i, 0)
+        barrier()
+        seen.clear()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for i in range(K):
+            step_e2e(W + i, 0)
+        m1.record()
+        barrier()
+        e2e_ms = max_over_ranks(m0.elapsed_time(m1))
+        e2e = {"value": world * B * K / (e2e_ms / 1e3), "unit": "samples/s",
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 * (1 + n_tasks),
+               "ms_per_step": e2e_ms / K,
+               "how": "pinned host batch -> cudaMemcpyAsync on a copy stream (double-buffered, "
+                      "overlapped with the previous step) -> cast kernel -> step; loss row written "
+                      "to pinned host memory by the criterion kernel and read by the host 2 steps late",
+               "losses_read": len(seen)}
+
+    # ======================= CPU baseline (rank 0, N=1) =======================
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = time_cpu_reference(args.algo, args.cpu_batch, args.cpu_steps, 1)
+        cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": total_ms / K, "step_p50_ms": statistics.median(step_ms),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if precision == Precision.BF16 else "f32", "data": "synthetic",
+                "config": {"workload": workload_name(B, args.algo), "global_batch": B * world,
+                           "parallelism": "dp%d" % world,
+                           "precision": "bf16 forward/backward + bf16 grads, fp32 master weights and "
+                                        "optimizer state" if precision == Precision.BF16 else "fp32",
+                           "l2": "no flush needed: each step streams the 54.7M-element arena "
+                                 "(>= 1.1 GB) and 4 rotating input batches, far larger than the 126 MB L2",
+                           "grad_allreduce": "NCCL in place on bf16 arena buckets" if world > 1 else "none (1 GPU)"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+                "clocks": clocks.summary(), "final_loss": float(losses[-1])}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        main_reference(args, rank)
+        return
+    if world != args.gpus:
+        log("note: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world))
+    main_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

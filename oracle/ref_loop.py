@@ -172,6 +172,23 @@ def uncertainty_criterion(loss_modules, kinds, names, log_variance, outputs, tar
 # the loop
 # ----------------------------------------------------------------------------------------------
 
+def reference_minibatch(model, criterion_fn, opt, model_params, gradient_clip, data, target,
+                        training=True):
+    """One pass of SolverWorker._pass_one_minibatch (solver_worker.py:533-594) on the CPU:
+    forward, criterion, NaN guard, zero_grad, backward, optional clip, optimizer step."""
+    output = model(data)
+    total, sub = criterion_fn(output, target)
+    if torch.isnan(total).any():
+        raise FloatingPointError("Losses become NaN")
+    if training:
+        opt.zero_grad()
+        total.backward()
+        if gradient_clip:
+            torch.nn.utils.clip_grad_norm_(model_params, gradient_clip)
+        opt.step()
+    return output, total, sub
+
+
 class Trace(NamedTuple):
     losses: Dict[Tuple[int, str], np.ndarray]     # (epoch, split) -> [n_minibatch, 1+T] fp32
     indices: Dict[Tuple[int, str], List[int]]     # (epoch, split) -> sample ids in trained order
