@@ -38,7 +38,7 @@ class TaskDesc(C.Structure):
 
 
 # name -> (restype, argtypes); every name here must be declared in include/frl_b200.h
-_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 SIGNATURES = {
     "frl_abi_version": (_i, []),
     "frl_last_error": (C.c_char_p, []),
@@ -46,9 +46,9 @@ SIGNATURES = {
     "frl_launch_count_reset": (None, []),
     "frl_device_sm_count": (_i, []),
     "frl_device_arch": (_i, []),
-    "frl_sgd_momentum": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _vp, _i, _i, _vp]),
-    "frl_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i64, _f, _vp, _i, _vp]),
-    "frl_rmsprop": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _vp, _i, _vp]),
+    "frl_sgd_momentum": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _vp, _i, _i, _vp]),
+    "frl_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i64, _d, _vp, _i, _vp]),
+    "frl_rmsprop": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _d, _vp, _i, _vp]),
     "frl_reduce_scratch_bytes": (_i64, []),
     "frl_grad_sumsq_clip": (_i, [_vp, _i64, _i, _f, _f, _vp, _vp, _vp]),
     "frl_criteria_scratch_bytes": (_i64, [_i]),

@@ -205,57 +205,64 @@ static int launch_update(const Rule& rule, float* p, const void* g, float* s0, f
 using namespace frl;
 
 extern "C" int frl_sgd_momentum(float* p, const void* g, float* buf, void* p_lp, int64_t n,
-                                float lr, float mu, float dampening, float wd,
-                                float grad_scale, const float* grad_scale_dev,
+                                double lr, double mu, double dampening, double wd,
+                                double grad_scale, const float* grad_scale_dev,
                                 int first_step, int g_dtype, void* stream) {
-    FRL_REQUIRE(mu == 0.f || buf != nullptr, FRL_E_ARG, "frl_sgd_momentum: momentum needs buf");
-    SgdRule r{-lr, mu, 1.f - dampening, wd, first_step ? 1 : 0, (mu != 0.f) ? 1 : 0};
+    FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_sgd_momentum: momentum needs buf");
+    SgdRule r{static_cast<float>(-lr), static_cast<float>(mu), static_cast<float>(1.0 - dampening),
+              static_cast<float>(wd), first_step ? 1 : 0, (mu != 0.0) ? 1 : 0};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (mu != 0.f)
-        return launch_update<SgdRule, 1>(r, p, g, buf, nullptr, nullptr, p_lp, n, grad_scale,
+    const float gs = static_cast<float>(grad_scale);
+    if (mu != 0.0)
+        return launch_update<SgdRule, 1>(r, p, g, buf, nullptr, nullptr, p_lp, n, gs,
                                          grad_scale_dev, g_dtype, st, "frl_sgd_momentum");
-    return launch_update<SgdRule, 0>(r, p, g, nullptr, nullptr, nullptr, p_lp, n, grad_scale,
+    return launch_update<SgdRule, 0>(r, p, g, nullptr, nullptr, nullptr, p_lp, n, gs,
                                      grad_scale_dev, g_dtype, st, "frl_sgd_momentum");
 }
 
 extern "C" int frl_adam(float* p, const void* g, float* m, float* v, float* vmax, void* p_lp,
-                        int64_t n, float lr, float beta1, float beta2, float eps, float wd,
-                        int64_t step, float grad_scale, const float* grad_scale_dev,
+                        int64_t n, double lr, double beta1, double beta2, double eps, double wd,
+                        int64_t step, double grad_scale, const float* grad_scale_dev,
                         int g_dtype, void* stream) {
     FRL_REQUIRE(m && v, FRL_E_ARG, "frl_adam: null state");
     FRL_REQUIRE(step >= 1, FRL_E_ARG, "frl_adam: step must be >= 1");
     // bias corrections in double, as torch computes them from Python floats
-    const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
-    const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
-    const float neg_step = static_cast<float>(-(static_cast<double>(lr) / bc1));
+    const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+    const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+    const float neg_step = static_cast<float>(-(lr / bc1));
     const float bc2s = static_cast<float>(sqrt(bc2));
-    const float w1 = static_cast<float>(1.0 - static_cast<double>(beta1));
-    const float w2 = static_cast<float>(1.0 - static_cast<double>(beta2));
+    const float w1 = static_cast<float>(1.0 - beta1);
+    const float w2 = static_cast<float>(1.0 - beta2);
+    const float b2 = static_cast<float>(beta2), epsf = static_cast<float>(eps), wdf = static_cast<float>(wd);
+    const float gs = static_cast<float>(grad_scale);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (vmax) {
-        AdamRule<true> r{w1, beta2, w2, eps, wd, neg_step, bc2s};
-        return launch_update<AdamRule<true>, 3>(r, p, g, m, v, vmax, p_lp, n, grad_scale,
+        AdamRule<true> r{w1, b2, w2, epsf, wdf, neg_step, bc2s};
+        return launch_update<AdamRule<true>, 3>(r, p, g, m, v, vmax, p_lp, n, gs,
                                                 grad_scale_dev, g_dtype, st, "frl_adam");
     }
-    AdamRule<false> r{w1, beta2, w2, eps, wd, neg_step, bc2s};
-    return launch_update<AdamRule<false>, 2>(r, p, g, m, v, nullptr, p_lp, n, grad_scale,
+    AdamRule<false> r{w1, b2, w2, epsf, wdf, neg_step, bc2s};
+    return launch_update<AdamRule<false>, 2>(r, p, g, m, v, nullptr, p_lp, n, gs,
                                              grad_scale_dev, g_dtype, st, "frl_adam");
 }
 
 extern "C" int frl_rmsprop(float* p, const void* g, float* sq, float* buf, void* p_lp, int64_t n,
-                           float lr, float alpha, float eps, float wd, float mu,
-                           float grad_scale, const float* grad_scale_dev, int g_dtype,
+                           double lr, double alpha, double eps, double wd, double mu,
+                           double grad_scale, const float* grad_scale_dev, int g_dtype,
                            void* stream) {
     FRL_REQUIRE(sq, FRL_E_ARG, "frl_rmsprop: null sq");
-    FRL_REQUIRE(mu == 0.f || buf != nullptr, FRL_E_ARG, "frl_rmsprop: momentum needs buf");
-    const float oma = static_cast<float>(1.0 - static_cast<double>(alpha));
+    FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_rmsprop: momentum needs buf");
+    const float af = static_cast<float>(alpha), oma = static_cast<float>(1.0 - alpha);
+    const float epsf = static_cast<float>(eps), wdf = static_cast<float>(wd);
+    const float muf = static_cast<float>(mu), nlr = static_cast<float>(-lr);
+    const float gs = static_cast<float>(grad_scale);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (mu != 0.f) {
-        RmspropRule<true> r{alpha, oma, eps, wd, mu, -lr};
-        return launch_update<RmspropRule<true>, 2>(r, p, g, sq, buf, nullptr, p_lp, n, grad_scale,
+    if (mu != 0.0) {
+        RmspropRule<true> r{af, oma, epsf, wdf, muf, nlr};
+        return launch_update<RmspropRule<true>, 2>(r, p, g, sq, buf, nullptr, p_lp, n, gs,
                                                    grad_scale_dev, g_dtype, st, "frl_rmsprop");
     }
-    RmspropRule<false> r{alpha, oma, eps, wd, mu, -lr};
-    return launch_update<RmspropRule<false>, 1>(r, p, g, sq, nullptr, nullptr, p_lp, n, grad_scale,
+    RmspropRule<false> r{af, oma, epsf, wdf, muf, nlr};
+    return launch_update<RmspropRule<false>, 1>(r, p, g, sq, nullptr, nullptr, p_lp, n, gs,
                                                 grad_scale_dev, g_dtype, st, "frl_rmsprop");
 }

@@ -157,6 +157,35 @@ def _aggregate_sample_summaries(results: List[SampleSummary]) -> SplitSampleSumm
         text="\n".join(texts) if texts else None, summaries=plots)
 
 
+def _cuda_device_count_without_poisoning_fork() -> int:
+    """Device count for the parent process.
+
+    ``torch.cuda.is_available()`` normally goes through ``cudaGetDeviceCount`` which arms torch's
+    fork guard: children forked afterwards cannot initialise CUDA ("Cannot re-initialize CUDA in
+    forked subprocess") — the stock reference trips over exactly this on current torch
+    (reference solver.py:740-747).  The NVML-based check leaves the process fork-safe."""
+    os.environ.setdefault("PYTORCH_NVML_BASED_CUDA_CHECK", "1")
+    if not torch.cuda.is_available():
+        return 0
+    return torch.cuda.device_count()
+
+
+def _fork_is_safe() -> bool:
+    """True if a forked child of this process can still initialise CUDA (probed in a throwaway
+    child, because the guard's state is only observable after the fork)."""
+    if torch.cuda.is_initialized():
+        return False
+    pid = os.fork()
+    if pid == 0:
+        code = 1
+        try:
+            code = 1 if torch._C._cuda_isInBadFork() else 0
+        finally:
+            os._exit(code)
+    _, status = os.waitpid(pid, 0)
+    return os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+
+
 def resolve_precision(explicit: Optional[Precision] = None) -> Precision:
     if explicit is not None:
         return explicit
@@ -440,15 +469,16 @@ class Solver:
     def solve(cls, run_opts: RunOpts, problem: Problem, *, group_name: Optional[str],
               init_method: str, node_idx: int = 0, node_count: int = 1, memory_quota: int = 0,
               precision: Optional[Precision] = None) -> Iterator[PerformanceSummary]:
-        if run_opts.cpuonly or not torch.cuda.is_available():
+        n_visible = 0 if run_opts.cpuonly else _cuda_device_count_without_poisoning_fork()
+        if n_visible == 0:
             raise RuntimeError(
-                "frl_b200 runs the training step on B200 GPUs only (cpuonly=%s, cuda available=%s);"
-                " there is no CPU path" % (run_opts.cpuonly, torch.cuda.is_available()))
+                "frl_b200 runs the training step on B200 GPUs only (cpuonly=%s, visible CUDA "
+                "devices=%d); there is no CPU path" % (run_opts.cpuonly, n_visible))
         run_device = Device.GPU
         if run_opts.singleThreaded:
             device_count, world_size = 1, 1
         else:
-            device_count = torch.cuda.device_count()
+            device_count = n_visible
             world_size = device_count * node_count
         logger.info("World size %d, device count %d" % (world_size, device_count))
         num_workers = min(device_count, world_size)
@@ -463,7 +493,10 @@ class Solver:
         logger.info("Parent process has pid " + str(os.getpid()))
         # fork keeps un-picklable Problems working (as in the reference) but is only safe while
         # this process holds no CUDA context
-        ctx = multiprocessing.get_context("spawn" if torch.cuda.is_initialized() else "fork")
+        use_fork = run_opts.singleThreaded or _fork_is_safe()
+        if not use_fork:
+            logger.info("CUDA already touched in the parent: ranks are spawned (Problem must pickle)")
+        ctx = multiprocessing.get_context("fork" if use_fork else "spawn")
         cleanup_flag = ctx.Event()
         processes, parent_pipes = [], []
         args: Optional[SolverWorkerArgs] = None

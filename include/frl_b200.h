@@ -53,26 +53,29 @@ int          frl_device_arch(void);
  *   grad_scale_dev  optional device scalar multiplied in as well (clip coefficient written
  *                   by frl_grad_sumsq_clip), NULL = 1
  * All arrays must be 16-byte aligned; n is arbitrary (scalar tail).
+ * Hyper-parameters are doubles (Python floats): derived constants such as 1-beta2 or the
+ * Adam bias corrections are formed in double and rounded to fp32 once, exactly as torch does
+ * when it hands Python scalars to fp32 tensor ops.
  * Update rules are torch 2.11's (L2-coupled weight decay: g += wd * p first).
  * ---------------------------------------------------------------------------------------- */
 
 /* SGD: buf = first_step ? g : mu*buf + (1-dampening)*g ; p -= lr*buf.   mu == 0: buf may be NULL. */
 int frl_sgd_momentum(float* p, const void* g, float* buf, void* p_lp, int64_t n,
-                     float lr, float mu, float dampening, float wd,
-                     float grad_scale, const float* grad_scale_dev,
+                     double lr, double mu, double dampening, double wd,
+                     double grad_scale, const float* grad_scale_dev,
                      int first_step, int g_dtype, void* stream);
 
 /* Adam (coupled L2, optional amsgrad when vmax != NULL).  `step` is the 1-based step count
  * used for the bias corrections (computed in double on the host side of the call). */
 int frl_adam(float* p, const void* g, float* m, float* v, float* vmax, void* p_lp, int64_t n,
-             float lr, float beta1, float beta2, float eps, float wd, int64_t step,
-             float grad_scale, const float* grad_scale_dev, int g_dtype, void* stream);
+             double lr, double beta1, double beta2, double eps, double wd, int64_t step,
+             double grad_scale, const float* grad_scale_dev, int g_dtype, void* stream);
 
 /* RMSprop (not centered): sq = alpha*sq + (1-alpha)*g^2 ; avg = sqrt(sq)+eps ;
  * mu > 0: buf = mu*buf + g/avg ; p -= lr*buf     else: p -= lr*g/avg  (buf may be NULL). */
 int frl_rmsprop(float* p, const void* g, float* sq, float* buf, void* p_lp, int64_t n,
-                float lr, float alpha, float eps, float wd, float mu,
-                float grad_scale, const float* grad_scale_dev, int g_dtype, void* stream);
+                double lr, double alpha, double eps, double wd, double mu,
+                double grad_scale, const float* grad_scale_dev, int g_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3 — global gradient norm for clipping.

@@ -42,8 +42,8 @@ def test_sgd_momentum_matches_oracle(n, gdt, lp):
         rp, rb = optim_np.sgd_step(rp, g_seen, rb, lr=0.05, mu=0.9, dampening=0.0, wd=1e-5,
                                    first_step=(step == 0), grad_scale=0.5)
     torch.cuda.synchronize()
-    np.testing.assert_allclose(p.cpu().numpy(), rp, rtol=2e-6, atol=1e-7)
-    np.testing.assert_allclose(buf.cpu().numpy(), rb, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(p.cpu().numpy(), rp, rtol=2e-6, atol=5e-7)
+    np.testing.assert_allclose(buf.cpu().numpy(), rb, rtol=2e-6, atol=5e-7)
     if lp:
         assert torch.equal(p_lp, p.to(torch.bfloat16))      # shadow = RNE(bf16) of the master
 
@@ -219,7 +219,7 @@ def test_fused_mse_and_ce_match_oracle(dt, tol, B, C):
     total, subs = criteria_np.weighted_total([l_mse, l_ce], [0.5, 2.0])
     np.testing.assert_allclose(res, [total] + subs, rtol=max(tol, 5e-6) if dt == torch.float32 else 2e-3)
     np.testing.assert_allclose(grads[0].float().cpu().numpy(), 0.5 * g_mse, rtol=tol * 4, atol=tol * 1e-2 + 1e-9)
-    np.testing.assert_allclose(grads[1].float().cpu().numpy(), 2.0 * g_ce, rtol=tol * 4, atol=tol * 1e-3 + 1e-9)
+    np.testing.assert_allclose(grads[1].float().cpu().numpy(), 2.0 * g_ce, rtol=tol * 4, atol=tol * 1e-3 + 2e-8)
 
 
 def test_fused_criterion_matches_torch_losses_exactly_in_structure():
