@@ -163,3 +163,18 @@ def test_multiprocess_entry_point_with_pipes(tmp_path):
                          timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MP_SOLVE_OK" in out.stdout
+
+
+def test_multi_gpu_pipeline_matches_oracle(tmp_path):
+    """>= 2 GPUs only: real kernels + NCCL bucket all-reduce vs the CPU oracle on the global batch."""
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    script = os.path.join(os.path.dirname(__file__), "run_ddp_vs_oracle.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                          "29533", script], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("DDP_PARITY_OK") == 3
