@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--cpu-steps", type=int, default=3, help="cpu_baseline leg: timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--bucket-mb", type=float, default=None, help="gradient bucket cap (MiB)")
+    ap.add_argument("--profile", default=None, help="write a torch.profiler chrome trace of 5 steps here")
     return ap.parse_args()
 
 
@@ -219,6 +221,8 @@ def main_b200(args, rank, local_rank, world):
                              save_dir=save_dir, run_device=Device.GPU, node_idx=0, node_count=1,
                              rank=rank, local_rank=local_rank, world_size=world, group_name=None,
                              init_method="env://", precision=precision)
+    if args.bucket_mb is not None:
+        os.environ["FRL_B200_BUCKET_MB"] = str(args.bucket_mb)
     worker, _, _ = Solver.build_worker(wargs)
     worker.model.train()
     worker.criterion.train()
@@ -250,7 +254,7 @@ def main_b200(args, rank, local_rank, world):
         return tv.item()
 
     W, K = args.warmup, args.steps
-    log_ring = LossLog(n_tasks, W + K + 8, dev)
+    log_ring = LossLog(n_tasks, W + K + 16, dev)
 
     def step_resident(i):
         data, target = pool[i % POOL]
@@ -267,9 +271,11 @@ def main_b200(args, rank, local_rank, world):
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     with ClockSampler(local_rank) as clocks:
         marks[0].record()
+        host_t0 = time.perf_counter()
         for i in range(K):
             step_resident(W + i)
             marks[i + 1].record()
+        host_issue_ms = 1e3 * (time.perf_counter() - host_t0) / K     # CPU time to ISSUE a step
         barrier()
     launches = _native.launch_count() - launches0
     worker.pipeline.record_update_events = False
@@ -303,6 +309,20 @@ def main_b200(args, rank, local_rank, world):
                 "elems_per_step": upd_elems // max(K, 1), "launches_per_step": len(upd) / max(K, 1),
                 "avg_launch_ms": (sum(upd_ms) / len(upd_ms)) if upd_ms else None,
                 "share_of_step": (sum(upd_ms) / K) / (total_ms / K) if upd_ms else None}
+
+    if args.profile:
+        # every rank runs the steps (collectives!); only rank 0 records
+        from contextlib import nullcontext
+        from torch.profiler import ProfilerActivity, profile
+        ctx = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) if rank == 0 else nullcontext()
+        with ctx as prof:
+            for i in range(5):
+                step_resident(W + K + i)
+            torch.cuda.synchronize()
+        if rank == 0:
+            prof.export_chrome_trace(args.profile)
+            log(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25))
+    barrier()
 
     # ======================= leg 2: end to end from host buffers =======================
     e2e = None
@@ -379,6 +399,7 @@ def main_b200(args, rank, local_rank, world):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": total_ms / K, "step_p50_ms": statistics.median(step_ms),
+                "host_issue_ms_per_step": host_issue_ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if precision == Precision.BF16 else "f32", "data": "synthetic",
                 "config": {"workload": workload_name(B, args.algo), "global_batch": B * world,

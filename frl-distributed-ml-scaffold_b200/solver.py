@@ -255,7 +255,8 @@ class Solver:
         if checkpoint:
             optimizer.load_state_dict(checkpoint.optimizerState)
         pipeline = GradBucketPipeline(arena, optimizer, world_size=args.world_size,
-                                      clip_norm=run_opts.optim.gradientClip)
+                                      clip_norm=run_opts.optim.gradientClip,
+                                      bucket_cap_mb=float(os.environ.get("FRL_B200_BUCKET_MB", "25")))
         buffers = None
         if distributed:
             pipeline.broadcast_parameters(src=0)

@@ -76,7 +76,9 @@ def main():
                     torch.nn.utils.clip_grad_norm_(ref.parameters(), clip)
                 ropt.step()
             want = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
-            np.testing.assert_allclose(mine.cpu().numpy(), want.numpy(), rtol=2e-4, atol=2e-6)
+            # Adam's m/(sqrt(v)+eps) amplifies fp32 rounding where v is tiny; a step moves a weight by ~lr
+            tol = dict(rtol=1e-3, atol=5e-5) if algo == "adam" else dict(rtol=2e-4, atol=2e-6)
+            np.testing.assert_allclose(mine.cpu().numpy(), want.numpy(), **tol)
             print("DDP_PARITY_OK", algo, clip, "world", world, flush=True)
         pipe.remove_hooks()
         dist.barrier()
