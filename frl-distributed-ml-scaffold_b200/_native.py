@@ -56,6 +56,8 @@ SIGNATURES = {
     "frl_criteria_backward": (_i, [C.POINTER(TaskDesc), _i, _vp, _vp, _vp, _vp]),
     "frl_preproc_affine": (_i, [_vp, _i, _vp, _i, _i64, _i64, _i64, _vp, _vp, _vp]),
     "frl_cast_scale": (_i, [_vp, _i, _vp, _i, _i64, _f, _vp]),
+    "frl_colsum_scratch_bytes": (_i64, [_i64, _i64]),
+    "frl_colsum": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i, _vp, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -198,3 +200,21 @@ def cast_scale(src, dst, scale: float = 1.0) -> None:
     assert dst.numel() == n and src.is_contiguous() and dst.is_contiguous()
     _check(lib().frl_cast_scale(_ptr(src), dtype_code(src.dtype), _ptr(dst),
                                 dtype_code(dst.dtype), n, scale, _stream()), "frl_cast_scale")
+
+
+# ---- K6 -------------------------------------------------------------------------------------
+
+_colsum_scratch = {}
+
+
+def colsum(x, out, accumulate: bool = False) -> None:
+    """out[c] (+)= sum_r x[r, c] for a contiguous 2-D ``x``; ``out`` may be an arena view."""
+    rows, cols = x.shape
+    key = (x.device.index, cols)
+    need = int(lib().frl_colsum_scratch_bytes(rows, cols))
+    buf = _colsum_scratch.get(key)
+    if buf is None or buf.numel() * 4 < need:
+        buf = _colsum_scratch[key] = torch.zeros((need + 3) // 4, dtype=torch.int32, device=x.device)
+    _check(lib().frl_colsum(_ptr(x), dtype_code(x.dtype), rows, cols, _ptr(out),
+                            dtype_code(out.dtype), int(accumulate), _ptr(buf), _stream()),
+           "frl_colsum")

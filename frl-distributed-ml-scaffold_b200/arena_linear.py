@@ -1,0 +1,112 @@
+"""``nn.Linear`` whose parameter gradients are born in the gradient arena.
+
+The reference lets autograd allocate ``weight.grad`` wherever the caching allocator pleases and
+DDP then copies it into a bucket, pre-divides, all-reduces and copies it back (reference
+solver.py:287-289 -> torch Reducer).  For exact ``nn.Linear`` modules — the layers where a
+Problem's forward really is a dense contraction — the solver swaps the module's ``forward`` for
+this autograd Function while the model is wrapped:
+
+  forward   y = x W^T + b                      (cuBLAS, unchanged)
+  backward  dX = dY W                          (cuBLAS)
+            dW = dY^T X   written by cuBLAS straight into the weight's slice of the grad arena
+            db = colsum(dY) by ``frl_colsum`` straight into the bias's slice
+
+so the bucket NCCL reduces is complete the moment the layer's backward returns: no flatten
+copy, no separate bias-reduction pass through a generic reduce kernel.  Outside a pipeline
+step (``autograd.grad`` calls of GradNorm / debugGrad) the Function returns ordinary gradients.
+"""
+import types
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _native
+
+KERNELS = _native
+
+
+class _ArenaLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, site):
+        ctx.site = site
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight)
+        return F.linear(x, weight, bias)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        site = ctx.site
+        dx = dy.matmul(weight) if ctx.needs_input_grad[0] else None
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        x2 = x.reshape(-1, x.shape[-1])
+        pipe = site.pipeline
+        if pipe is not None and pipe.step_open:
+            first = site.touched_step != pipe.step_id
+            site.touched_step = pipe.step_id
+            gw = pipe.arena.grad_view(site.wslot)
+            if first:
+                torch.mm(dy2.t(), x2, out=gw)
+            else:
+                gw.addmm_(dy2.t(), x2)
+            pipe.mark_ready(site.wslot)
+            if ctx.has_bias and site.bslot is not None:
+                if not dy2.is_contiguous():
+                    dy2 = dy2.contiguous()
+                KERNELS.colsum(dy2, pipe.arena.grad_view(site.bslot), accumulate=not first)
+                pipe.mark_ready(site.bslot)
+            return dx, None, None, None
+        dw = dy2.t().mm(x2) if ctx.needs_input_grad[1] else None
+        db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db, None
+
+
+class LinearSite:
+    """Per-module bookkeeping: arena slots of weight/bias and the owning pipeline."""
+    __slots__ = ("module", "wslot", "bslot", "pipeline", "touched_step")
+
+    def __init__(self, module, wslot, bslot, pipeline):
+        self.module = module
+        self.wslot = wslot
+        self.bslot = bslot
+        self.pipeline = pipeline
+        self.touched_step = -1
+
+
+def _forward(self, x):
+    return _ArenaLinearFn.apply(x, self.weight, self.bias, self._frl_site)
+
+
+def patch_linears(model: nn.Module, pipeline) -> List[LinearSite]:
+    """Route every exact ``nn.Linear`` whose weight lives in the arena through the Function."""
+    sites: List[LinearSite] = []
+    arena = pipeline.arena
+    for mod in model.modules():
+        if type(mod) is not nn.Linear or "forward" in mod.__dict__:
+            continue
+        if id(mod.weight) not in arena._by_id or not mod.weight.is_cuda:
+            continue
+        wslot = arena.slot_of(mod.weight)
+        bslot = arena.slot_of(mod.bias) if (mod.bias is not None and id(mod.bias) in arena._by_id) else None
+        if mod.bias is not None and bslot is None:
+            continue                     # frozen bias: leave the module alone
+        site = LinearSite(mod, wslot, bslot, pipeline)
+        mod._frl_site = site
+        mod.forward = types.MethodType(_forward, mod)
+        sites.append(site)
+    return sites
+
+
+def unpatch_linears(sites: List[LinearSite]) -> None:
+    for site in sites:
+        site.module.__dict__.pop("forward", None)
+        site.module.__dict__.pop("_frl_site", None)
+
+
+def repatch_linears(sites: List[LinearSite]) -> None:
+    for site in sites:
+        site.module._frl_site = site
+        site.module.forward = types.MethodType(_forward, site.module)

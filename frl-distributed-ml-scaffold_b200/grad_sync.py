@@ -50,13 +50,15 @@ class GradBucketPipeline:
         self.clip_norm = float(clip_norm or 0.0)
         self.grad_scale = 1.0 / world_size
         self.distributed = world_size > 1
-        # eager: update a bucket as soon as it is reduced (needs no global norm)
-        self.eager = eager_update and self.clip_norm == 0.0 and self.distributed
         self.on_cuda = arena.device.type == "cuda"
+        # eager: update a bucket on the side stream as soon as it is complete (and reduced) while
+        # backward is still running — HBM-bound update under compute-bound GEMMs.  Needs no
+        # global norm, so clipping turns it off.
+        self.eager = eager_update and self.clip_norm == 0.0 and (self.distributed or self.on_cuda)
 
         cap = int(bucket_cap_mb * 1024 * 1024)
         first = int(first_bucket_mb * 1024 * 1024) if (first_bucket_mb and self.distributed) else None
-        ranges = arena.buckets(cap, first) if self.distributed else [(0, arena.numel)]
+        ranges = arena.buckets(cap, first) if (self.distributed or self.eager) else [(0, arena.numel)]
         self.buckets: List[_Bucket] = [_Bucket(lo, hi) for lo, hi in ranges]
         self._bucket_of = {}
         for s in arena.slots:
@@ -80,6 +82,8 @@ class GradBucketPipeline:
             nbytes = KERNELS.reduce_scratch_bytes()
             self.clip_scratch = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=arena.device)
         self._step_open = False
+        self.step_id = 0
+        self.linear_sites = []
         # timing taps (bench): list of (start_event, end_event, lo, hi) for update launches
         self.record_update_events = False
         self.update_events: List[Tuple[torch.cuda.Event, torch.cuda.Event, int, int]] = []
@@ -94,7 +98,12 @@ class GradBucketPipeline:
             b.work = None
             b.launched = False
         self.optimizer.begin_step()
+        self.step_id += 1
         self._step_open = True
+
+    @property
+    def step_open(self) -> bool:
+        return self._step_open
 
     def _make_hook(self, slot) -> Callable[[nn.Parameter], None]:
         def hook(param: nn.Parameter) -> None:
@@ -114,23 +123,28 @@ class GradBucketPipeline:
         self._ready += 1
         b = self._bucket_of[id(slot.param)]
         b.pending -= 1
-        if b.pending == 0 and self.distributed:
+        if b.pending == 0 and (self.distributed or self.eager):
             self._launch_bucket(b)
 
     def _launch_bucket(self, b: _Bucket) -> None:
-        view = self.arena.grad[b.lo:b.hi]
+        """Bucket complete: (all-reduce it and) update it on the side stream, behind everything
+        the compute stream has issued so far.  Runs in the autograd thread, so it is kept lean:
+        no context managers, one event."""
         if self.on_cuda:
-            self.side_stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.side_stream):
-                b.work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            cur = torch.cuda.current_stream()
+            self.side_stream.wait_stream(cur)
+            torch.cuda.set_stream(self.side_stream)
+        try:
+            if self.distributed:
+                b.work = dist.all_reduce(self.arena.grad[b.lo:b.hi], op=dist.ReduceOp.SUM,
+                                         group=self.pg, async_op=True)
                 if self.eager:
-                    b.work.wait()             # stream-level wait, host does not block
-                    self._update(b.lo, b.hi, None)
-        else:
-            b.work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                    b.work.wait()             # stream-level wait, the host does not block
             if self.eager:
-                b.work.wait()
                 self._update(b.lo, b.hi, None)
+        finally:
+            if self.on_cuda:
+                torch.cuda.set_stream(cur)
         b.launched = True
 
     def _update(self, lo: int, hi: int, coef) -> None:
@@ -157,20 +171,22 @@ class GradBucketPipeline:
                 raise RuntimeError(
                     "Expected to have finished reduction for every parameter, but parameters at "
                     f"indices {missing} did not receive a gradient in this step")
+            if self.eager and self.on_cuda:
+                torch.cuda.current_stream().wait_stream(self.side_stream)
             self._finish_partial(missing)
             return
-        if self.distributed:
+        if self.distributed or self.eager:
             if self.on_cuda:
                 cur = torch.cuda.current_stream()
-                if not self.eager:
-                    with torch.cuda.stream(self.side_stream):
-                        for b in self.buckets:
-                            b.work.wait()
-                cur.wait_stream(self.side_stream)
-            else:
-                if not self.eager:
+                if self.distributed and not self.eager:
+                    torch.cuda.set_stream(self.side_stream)
                     for b in self.buckets:
                         b.work.wait()
+                    torch.cuda.set_stream(cur)
+                cur.wait_stream(self.side_stream)
+            elif self.distributed and not self.eager:
+                for b in self.buckets:
+                    b.work.wait()
             if not self.eager:
                 self._tail_update()
         else:
@@ -191,6 +207,7 @@ class GradBucketPipeline:
         """world_size == 1 and some parameters got no gradient: torch.optim skips those (no
         weight decay, no momentum decay), so update only the contiguous runs that did."""
         skip = set(missing)
+        done = [(b.lo, b.hi) for b in self.buckets if b.launched and self.eager]
         coef = None
         if self.clip_norm > 0.0:
             for s in self.arena.slots:
@@ -204,7 +221,7 @@ class GradBucketPipeline:
         run_lo = None
         prev_end = None
         for s in self.arena.slots:
-            if s.index in skip:
+            if s.index in skip or any(lo <= s.offset < hi for lo, hi in done):
                 if run_lo is not None:
                     self._update(run_lo, prev_end, coef)
                     run_lo = None
@@ -228,6 +245,21 @@ class GradBucketPipeline:
         for h in self._handles:
             h.remove()
         self._handles = []
+        self.unpatch_linears()
+
+    # -- nn.Linear gradients written directly into the arena ---------------------------------------
+    def patch_linears(self, model: nn.Module) -> int:
+        from .arena_linear import patch_linears
+        self.linear_sites = patch_linears(model, self)
+        return len(self.linear_sites)
+
+    def unpatch_linears(self) -> None:
+        from .arena_linear import unpatch_linears
+        unpatch_linears(self.linear_sites)
+
+    def repatch_linears(self) -> None:
+        from .arena_linear import repatch_linears
+        repatch_linears(self.linear_sites)
 
 
 class BufferBroadcaster:

@@ -254,9 +254,16 @@ class Solver:
         optimizer = create_fused_optimizer(arena, run_opts.optim)
         if checkpoint:
             optimizer.load_state_dict(checkpoint.optimizerState)
-        pipeline = GradBucketPipeline(arena, optimizer, world_size=args.world_size,
-                                      clip_norm=run_opts.optim.gradientClip,
-                                      bucket_cap_mb=float(os.environ.get("FRL_B200_BUCKET_MB", "25")))
+        pipeline = GradBucketPipeline(
+            arena, optimizer, world_size=args.world_size, clip_norm=run_opts.optim.gradientClip,
+            bucket_cap_mb=float(os.environ.get("FRL_B200_BUCKET_MB", "48")), first_bucket_mb=None,
+            eager_update=os.environ.get("FRL_B200_EAGER_UPDATE", "1") != "0")
+        # GradNorm differentiates through the layers' backward (create_graph=True) and debugGrad
+        # calls autograd.grad on them: those runs keep the stock nn.Linear autograd path
+        from .criteria import GradNormWeightedCriterion
+        if (os.environ.get("FRL_B200_DIRECT_GRADS", "1") != "0" and not run_opts.debugGrad
+                and not isinstance(criterion, GradNormWeightedCriterion)):
+            pipeline.patch_linears(model)
         buffers = None
         if distributed:
             pipeline.broadcast_parameters(src=0)

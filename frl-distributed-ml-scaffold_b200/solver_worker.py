@@ -546,10 +546,14 @@ class SolverWorker:
         if self._serialize_state and self._state_wanted:
             was_training = self.model.training
             self.model.eval()
-            with self.arena.exported(cpu=True):
-                with io.BytesIO() as buf:
-                    torch.save(self.model, buf)
-                    model_bytes = buf.getvalue()
+            self.pipeline.unpatch_linears()          # pickle plain nn.Linear modules
+            try:
+                with self.arena.exported(cpu=True):
+                    with io.BytesIO() as buf:
+                        torch.save(self.model, buf)
+                        model_bytes = buf.getvalue()
+            finally:
+                self.pipeline.repatch_linears()
             with io.BytesIO() as buf:
                 state = self.optimizer.state_dict()
                 for entry in state["state"].values():

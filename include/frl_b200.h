@@ -152,6 +152,17 @@ int frl_preproc_affine(const void* src, int src_dtype, void* dst, int dst_dtype,
 int frl_cast_scale(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
                    float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K6 — column sum: out[c] (+)= sum_r x[r, c], x row-major [rows, cols].
+ * The bias gradient of a linear layer, written straight into the gradient arena; replaces the
+ * generic reduction autograd runs inside `total_loss.backward()` (reference
+ * solver_worker.py:586).  accumulate != 0 adds to `out` (a layer applied twice in one step).
+ * scratch: frl_colsum_scratch_bytes(rows, cols) bytes, zero-initialised once; deterministic.
+ * ---------------------------------------------------------------------------------------- */
+int64_t frl_colsum_scratch_bytes(int64_t rows, int64_t cols);
+int frl_colsum(const void* x, int x_dtype, int64_t rows, int64_t cols, void* out, int out_dtype,
+               int accumulate, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

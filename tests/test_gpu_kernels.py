@@ -366,3 +366,63 @@ def test_launch_counter_counts_our_kernels():
     assert _native.launch_count() == 3
     assert _native.lib().frl_device_arch() == 100
     assert _native.lib().frl_device_sm_count() == 148
+
+
+# ------------------------------------------------------------------------------------------------
+# K6 + nn.Linear gradients born in the arena
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (7, 13), (4096, 4096), (4096, 1000), (333, 264), (5, 4104)])
+@pytest.mark.parametrize("xdt,odt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                     (torch.bfloat16, torch.float32)])
+def test_colsum_matches_float64_sum(rows, cols, xdt, odt):
+    x = torch.randn(rows, cols, device=DEV).to(xdt)
+    out = torch.full((cols,), 3.0, dtype=odt, device=DEV)
+    want = x.double().sum(0)
+    _native.colsum(x, out)
+    tol = dict(rtol=2e-2, atol=2e-1) if odt == torch.bfloat16 else dict(rtol=1e-5, atol=1e-4 * max(rows, 1) ** 0.5)
+    torch.testing.assert_close(out.double(), want, **tol)
+    before = out.clone()
+    _native.colsum(x, out, accumulate=True)
+    torch.testing.assert_close(out.double(), before.double() + want, **tol)
+    _native.colsum(x, out)                        # deterministic: same bits on a second launch
+    again = out.clone()
+    _native.colsum(x, out)
+    assert torch.equal(out, again)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_linear_gradients_are_written_into_the_arena(precision):
+    import torch.nn as nn
+    from frl_b200 import fused_optim, grad_sync
+    from frl_b200.arena import ParamArena
+    from frl_b200.types import OptAlgorithm, OptimOpts, Precision
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def build():
+        torch.manual_seed(0)
+        return nn.Sequential(nn.Linear(40, 64), nn.ReLU(), nn.Linear(64, 64), nn.ReLU(),
+                             nn.Linear(64, 8)).to(DEV)
+    plain, fancy = build(), build()
+    prec = Precision(precision)
+    results = []
+    for net, direct in ((plain, False), (fancy, True)):
+        arena = ParamArena(net.parameters(), device=DEV, precision=prec)
+        opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm.SGD, lr=0.05))
+        pipe = grad_sync.GradBucketPipeline(arena, opt, bucket_cap_mb=0.004, eager_update=direct)
+        if direct:
+            assert pipe.patch_linears(net) == 3 and len(pipe.buckets) > 1
+        x = torch.randn(32, 40, device=DEV)
+        x = x.to(torch.bfloat16) if prec == Precision.BF16 else x
+        for _ in range(3):
+            pipe.begin_step()
+            net(x).float().square().mean().backward()
+            pipe.finish_step()
+        torch.cuda.synchronize()
+        results.append((arena.grad.float().clone(), arena.master.clone()))
+        pipe.remove_hooks()
+    tol = dict(rtol=2e-2, atol=2e-3) if prec == Precision.BF16 else dict(rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(results[1][0], results[0][0], **tol)      # same gradients
+    torch.testing.assert_close(results[1][1], results[0][1], **tol)      # same weights after 3 steps
+    assert "forward" not in fancy[0].__dict__                            # unpatched again
