@@ -52,8 +52,9 @@ class GradBucketPipeline:
         self.distributed = world_size > 1
         self.on_cuda = arena.device.type == "cuda"
         # eager: update a bucket on the side stream as soon as it is complete (and reduced) while
-        # backward is still running — HBM-bound update under compute-bound GEMMs.  Needs no
-        # global norm, so clipping turns it off.
+        # backward is still running.  Needs no global norm, so clipping turns it off.  On one GPU
+        # the caller decides (measured on B200: the persistent cuBLAS GEMMs leave the update no
+        # SMs to overlap on, so a single tail launch is faster and cheaper to issue).
         self.eager = eager_update and self.clip_norm == 0.0 and (self.distributed or self.on_cuda)
 
         cap = int(bucket_cap_mb * 1024 * 1024)

@@ -257,7 +257,8 @@ class Solver:
         pipeline = GradBucketPipeline(
             arena, optimizer, world_size=args.world_size, clip_norm=run_opts.optim.gradientClip,
             bucket_cap_mb=float(os.environ.get("FRL_B200_BUCKET_MB", "48")), first_bucket_mb=None,
-            eager_update=os.environ.get("FRL_B200_EAGER_UPDATE", "1") != "0")
+            eager_update=os.environ.get("FRL_B200_EAGER_UPDATE",
+                                        "1" if args.world_size > 1 else "0") != "0")
         # GradNorm differentiates through the layers' backward (create_graph=True) and debugGrad
         # calls autograd.grad on them: those runs keep the stock nn.Linear autograd path
         from .criteria import GradNormWeightedCriterion

@@ -406,6 +406,7 @@ def test_linear_gradients_are_written_into_the_arena(precision):
                              nn.Linear(64, 8)).to(DEV)
     plain, fancy = build(), build()
     prec = Precision(precision)
+    x0 = torch.randn(32, 40, device=DEV)
     results = []
     for net, direct in ((plain, False), (fancy, True)):
         arena = ParamArena(net.parameters(), device=DEV, precision=prec)
@@ -413,8 +414,7 @@ def test_linear_gradients_are_written_into_the_arena(precision):
         pipe = grad_sync.GradBucketPipeline(arena, opt, bucket_cap_mb=0.004, eager_update=direct)
         if direct:
             assert pipe.patch_linears(net) == 3 and len(pipe.buckets) > 1
-        x = torch.randn(32, 40, device=DEV)
-        x = x.to(torch.bfloat16) if prec == Precision.BF16 else x
+        x = x0.to(torch.bfloat16) if prec == Precision.BF16 else x0
         for _ in range(3):
             pipe.begin_step()
             net(x).float().square().mean().backward()
