@@ -46,9 +46,9 @@ SIGNATURES = {
     "frl_launch_count_reset": (None, []),
     "frl_device_sm_count": (_i, []),
     "frl_device_arch": (_i, []),
-    "frl_sgd_momentum": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _vp, _i, _i, _vp]),
-    "frl_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i64, _d, _vp, _i, _vp]),
-    "frl_rmsprop": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _d, _vp, _i, _vp]),
+    "frl_sgd_momentum": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _vp, _vp, _i, _i, _vp]),
+    "frl_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i64, _d, _vp, _vp, _i, _vp]),
+    "frl_rmsprop": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _d, _vp, _vp, _i, _vp]),
     "frl_reduce_scratch_bytes": (_i64, []),
     "frl_grad_sumsq_clip": (_i, [_vp, _i64, _i, _f, _f, _vp, _vp, _vp]),
     "frl_criteria_scratch_bytes": (_i64, [_i]),
@@ -130,23 +130,23 @@ def launch_count_reset() -> None:
 # ---- K2 -------------------------------------------------------------------------------------
 
 def sgd_momentum(p, g, buf, p_lp, n, *, lr, mu, dampening, wd, grad_scale=1.0,
-                 grad_scale_dev=None, first_step=False) -> None:
+                 grad_scale_dev=None, first_step=False, dyn=None) -> None:
     _check(lib().frl_sgd_momentum(_ptr(p), _ptr(g), _ptr(buf), _ptr(p_lp), n, lr, mu, dampening,
-                                  wd, grad_scale, _ptr(grad_scale_dev), int(first_step),
+                                  wd, grad_scale, _ptr(grad_scale_dev), _ptr(dyn), int(first_step),
                                   dtype_code(g.dtype), _stream()), "frl_sgd_momentum")
 
 
 def adam(p, g, m, v, vmax, p_lp, n, *, lr, beta1, beta2, eps, wd, step, grad_scale=1.0,
-         grad_scale_dev=None) -> None:
+         grad_scale_dev=None, dyn=None) -> None:
     _check(lib().frl_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(vmax), _ptr(p_lp), n, lr,
-                          beta1, beta2, eps, wd, step, grad_scale, _ptr(grad_scale_dev),
+                          beta1, beta2, eps, wd, step, grad_scale, _ptr(grad_scale_dev), _ptr(dyn),
                           dtype_code(g.dtype), _stream()), "frl_adam")
 
 
 def rmsprop(p, g, sq, buf, p_lp, n, *, lr, alpha, eps, wd, mu, grad_scale=1.0,
-            grad_scale_dev=None) -> None:
+            grad_scale_dev=None, dyn=None) -> None:
     _check(lib().frl_rmsprop(_ptr(p), _ptr(g), _ptr(sq), _ptr(buf), _ptr(p_lp), n, lr, alpha,
-                             eps, wd, mu, grad_scale, _ptr(grad_scale_dev),
+                             eps, wd, mu, grad_scale, _ptr(grad_scale_dev), _ptr(dyn),
                              dtype_code(g.dtype), _stream()), "frl_rmsprop")
 
 

@@ -26,6 +26,7 @@ struct SgdRule {
     float neg_lr, mu, one_minus_damp, wd;
     int first_step, has_buf;
     static constexpr int kStates = 1;
+    __device__ __forceinline__ void patch(const float* dyn) { neg_lr = -__ldg(dyn); }
     __device__ __forceinline__ void operator()(float& p, float g, float& buf, float&, float&) const {
         g = fmaf(wd, p, g);
         if (has_buf) {
@@ -44,6 +45,10 @@ struct AdamRule {
     float neg_step_size;    // -lr / (1 - beta1^t)
     float bc2_sqrt;         // sqrt(1 - beta2^t)
     static constexpr int kStates = AMSGRAD ? 3 : 2;
+    __device__ __forceinline__ void patch(const float* dyn) {
+        neg_step_size = __ldg(dyn);
+        bc2_sqrt = __ldg(dyn + 1);
+    }
     __device__ __forceinline__ void operator()(float& p, float g, float& m, float& v, float& vmax) const {
         g = fmaf(wd, p, g);
         m = fmaf(w1, g - m, m);                       // exp_avg.lerp_(g, 1-beta1), weight < 0.5 branch
@@ -59,6 +64,7 @@ template <bool MOMENTUM>
 struct RmspropRule {
     float alpha, one_minus_alpha, eps, wd, mu, neg_lr;
     static constexpr int kStates = MOMENTUM ? 2 : 1;
+    __device__ __forceinline__ void patch(const float* dyn) { neg_lr = -__ldg(dyn); }
     __device__ __forceinline__ void operator()(float& p, float g, float& sq, float& buf, float&) const {
         g = fmaf(wd, p, g);
         sq = fmaf(one_minus_alpha * g, g, sq * alpha);
@@ -96,7 +102,9 @@ template <typename Rule, typename GVec, int NS, bool HAS_LP>
 __global__ void __launch_bounds__(kThreads)
 update_kernel(float* __restrict__ p_, const GVec* __restrict__ g, float* __restrict__ s0_,
               float* __restrict__ s1_, float* __restrict__ s2_, bf16x4* __restrict__ lp,
-              int64_t n, Rule rule, float gscale, const float* __restrict__ gscale_dev) {
+              int64_t n, Rule rule, float gscale, const float* __restrict__ gscale_dev,
+              const float* __restrict__ dyn) {
+    if (dyn) rule.patch(dyn);      // per-step scalars from device memory (CUDA-graph replays)
     f32x4* p = reinterpret_cast<f32x4*>(p_);
     f32x4* s0 = reinterpret_cast<f32x4*>(s0_);
     f32x4* s1 = reinterpret_cast<f32x4*>(s1_);
@@ -183,7 +191,7 @@ static int grid_for(K kernel, int64_t n) {
 template <typename Rule, int NS>
 static int launch_update(const Rule& rule, float* p, const void* g, float* s0, float* s1, float* s2,
                          void* p_lp, int64_t n, float gscale, const float* gscale_dev,
-                         int g_dtype, cudaStream_t st, const char* name) {
+                         const float* dyn, int g_dtype, cudaStream_t st, const char* name) {
     FRL_REQUIRE(n >= 0, FRL_E_ARG, "%s: n < 0", name);
     if (n == 0) return 0;
     FRL_REQUIRE(p && g, FRL_E_ARG, "%s: null p/g", name);
@@ -193,7 +201,7 @@ static int launch_update(const Rule& rule, float* p, const void* g, float* s0, f
     bf16x4* lp = static_cast<bf16x4*>(p_lp);
 #define FRL_LAUNCH(GV, LP)                                                                      \
     update_kernel<Rule, GV, NS, LP><<<grid_for(update_kernel<Rule, GV, NS, LP>, n), kThreads, 0, st>>>( \
-        p, static_cast<const GV*>(g), s0, s1, s2, lp, n, rule, gscale, gscale_dev)
+        p, static_cast<const GV*>(g), s0, s1, s2, lp, n, rule, gscale, gscale_dev, dyn)
     if (g_dtype == FRL_F32) { if (lp) FRL_LAUNCH(f32x4, true); else FRL_LAUNCH(f32x4, false); }
     else                    { if (lp) FRL_LAUNCH(bf16x4, true); else FRL_LAUNCH(bf16x4, false); }
 #undef FRL_LAUNCH
@@ -207,7 +215,7 @@ using namespace frl;
 extern "C" int frl_sgd_momentum(float* p, const void* g, float* buf, void* p_lp, int64_t n,
                                 double lr, double mu, double dampening, double wd,
                                 double grad_scale, const float* grad_scale_dev,
-                                int first_step, int g_dtype, void* stream) {
+                                const float* dyn, int first_step, int g_dtype, void* stream) {
     FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_sgd_momentum: momentum needs buf");
     SgdRule r{static_cast<float>(-lr), static_cast<float>(mu), static_cast<float>(1.0 - dampening),
               static_cast<float>(wd), first_step ? 1 : 0, (mu != 0.0) ? 1 : 0};
@@ -215,15 +223,15 @@ extern "C" int frl_sgd_momentum(float* p, const void* g, float* buf, void* p_lp,
     const float gs = static_cast<float>(grad_scale);
     if (mu != 0.0)
         return launch_update<SgdRule, 1>(r, p, g, buf, nullptr, nullptr, p_lp, n, gs,
-                                         grad_scale_dev, g_dtype, st, "frl_sgd_momentum");
+                                         grad_scale_dev, dyn, g_dtype, st, "frl_sgd_momentum");
     return launch_update<SgdRule, 0>(r, p, g, nullptr, nullptr, nullptr, p_lp, n, gs,
-                                     grad_scale_dev, g_dtype, st, "frl_sgd_momentum");
+                                     grad_scale_dev, dyn, g_dtype, st, "frl_sgd_momentum");
 }
 
 extern "C" int frl_adam(float* p, const void* g, float* m, float* v, float* vmax, void* p_lp,
                         int64_t n, double lr, double beta1, double beta2, double eps, double wd,
                         int64_t step, double grad_scale, const float* grad_scale_dev,
-                        int g_dtype, void* stream) {
+                        const float* dyn, int g_dtype, void* stream) {
     FRL_REQUIRE(m && v, FRL_E_ARG, "frl_adam: null state");
     FRL_REQUIRE(step >= 1, FRL_E_ARG, "frl_adam: step must be >= 1");
     // bias corrections in double, as torch computes them from Python floats
@@ -239,17 +247,17 @@ extern "C" int frl_adam(float* p, const void* g, float* m, float* v, float* vmax
     if (vmax) {
         AdamRule<true> r{w1, b2, w2, epsf, wdf, neg_step, bc2s};
         return launch_update<AdamRule<true>, 3>(r, p, g, m, v, vmax, p_lp, n, gs,
-                                                grad_scale_dev, g_dtype, st, "frl_adam");
+                                                grad_scale_dev, dyn, g_dtype, st, "frl_adam");
     }
     AdamRule<false> r{w1, b2, w2, epsf, wdf, neg_step, bc2s};
     return launch_update<AdamRule<false>, 2>(r, p, g, m, v, nullptr, p_lp, n, gs,
-                                             grad_scale_dev, g_dtype, st, "frl_adam");
+                                             grad_scale_dev, dyn, g_dtype, st, "frl_adam");
 }
 
 extern "C" int frl_rmsprop(float* p, const void* g, float* sq, float* buf, void* p_lp, int64_t n,
                            double lr, double alpha, double eps, double wd, double mu,
-                           double grad_scale, const float* grad_scale_dev, int g_dtype,
-                           void* stream) {
+                           double grad_scale, const float* grad_scale_dev, const float* dyn,
+                           int g_dtype, void* stream) {
     FRL_REQUIRE(sq, FRL_E_ARG, "frl_rmsprop: null sq");
     FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_rmsprop: momentum needs buf");
     const float af = static_cast<float>(alpha), oma = static_cast<float>(1.0 - alpha);
@@ -260,9 +268,9 @@ extern "C" int frl_rmsprop(float* p, const void* g, float* sq, float* buf, void*
     if (mu != 0.0) {
         RmspropRule<true> r{af, oma, epsf, wdf, muf, nlr};
         return launch_update<RmspropRule<true>, 2>(r, p, g, sq, buf, nullptr, p_lp, n, gs,
-                                                   grad_scale_dev, g_dtype, st, "frl_rmsprop");
+                                                   grad_scale_dev, dyn, g_dtype, st, "frl_rmsprop");
     }
     RmspropRule<false> r{af, oma, epsf, wdf, muf, nlr};
     return launch_update<RmspropRule<false>, 1>(r, p, g, sq, nullptr, nullptr, p_lp, n, gs,
-                                                grad_scale_dev, g_dtype, st, "frl_rmsprop");
+                                                grad_scale_dev, dyn, g_dtype, st, "frl_rmsprop");
 }

@@ -32,6 +32,32 @@ class FusedArenaOptimizer(torch.optim.Optimizer):
         self._vec: Dict[str, torch.Tensor] = {}
         self._steps = 0                # completed optimizer steps
         self._in_step = False
+        # device-resident per-step scalars (lr, Adam bias corrections): set when the step is
+        # replayed from a CUDA graph, where by-value kernel arguments are frozen at capture
+        self._dyn: Optional[torch.Tensor] = None
+        self._dyn_last: Optional[Tuple[float, ...]] = None
+
+    # -- device-resident scalars -----------------------------------------------------------------
+    def _dyn_values(self) -> Tuple[float, ...]:
+        """Scalars of the NEXT step (``_steps + 1``) in the layout the kernel's ``dyn`` expects."""
+        return (float(self.hyper["lr"]),)
+
+    def enable_dynamic_scalars(self) -> None:
+        if self._dyn is None:
+            self._dyn = torch.zeros(4, dtype=torch.float32, device=self.arena.device)
+            self._dyn_last = None
+        self.refresh_dynamic_scalars()
+
+    def refresh_dynamic_scalars(self) -> None:
+        """Upload the scalars if they changed (a 16-byte pageable copy: stream-ordered, and the
+        host buffer is consumed before the call returns)."""
+        if self._dyn is None:
+            return
+        vals = self._dyn_values()
+        if vals != self._dyn_last:
+            host = torch.tensor(list(vals) + [0.0] * (4 - len(vals)), dtype=torch.float32)
+            self._dyn.copy_(host)
+            self._dyn_last = vals
 
     # -- state vectors ---------------------------------------------------------------------------
     def _state(self, name: str) -> torch.Tensor:
@@ -154,7 +180,7 @@ class FusedSGD(FusedArenaOptimizer):
         KERNELS.sgd_momentum(p, g, buf, lp, hi - lo, lr=float(h["lr"]), mu=mu,
                              dampening=float(h["dampening"]), wd=float(h["weight_decay"]),
                              grad_scale=grad_scale, grad_scale_dev=coef,
-                             first_step=(self._steps == 0))
+                             first_step=(self._steps == 0), dyn=self._dyn)
 
 
 class FusedAdam(FusedArenaOptimizer):
@@ -170,6 +196,13 @@ class FusedAdam(FusedArenaOptimizer):
     def _per_param_extra(self):
         return {"step": torch.tensor(float(self._steps))}
 
+    def _dyn_values(self):
+        h = self.hyper
+        step = self._steps + 1
+        bc1 = 1.0 - float(h["betas"][0]) ** step
+        bc2 = 1.0 - float(h["betas"][1]) ** step
+        return (-(float(h["lr"]) / bc1), bc2 ** 0.5)
+
     def _launch(self, lo, hi, grad_scale, coef):
         h = self.hyper
         p, g, lp = self._slices(lo, hi)
@@ -178,7 +211,7 @@ class FusedAdam(FusedArenaOptimizer):
                      lp, hi - lo, lr=float(h["lr"]), beta1=float(h["betas"][0]),
                      beta2=float(h["betas"][1]), eps=float(h["eps"]),
                      wd=float(h["weight_decay"]), step=self._steps + 1,
-                     grad_scale=grad_scale, grad_scale_dev=coef)
+                     grad_scale=grad_scale, grad_scale_dev=coef, dyn=self._dyn)
 
 
 class FusedRMSprop(FusedArenaOptimizer):
@@ -200,7 +233,7 @@ class FusedRMSprop(FusedArenaOptimizer):
         KERNELS.rmsprop(p, g, self._state("square_avg")[lo:hi], buf, lp, hi - lo,
                         lr=float(h["lr"]), alpha=float(h["alpha"]), eps=float(h["eps"]),
                         wd=float(h["weight_decay"]), mu=mu, grad_scale=grad_scale,
-                        grad_scale_dev=coef)
+                        grad_scale_dev=coef, dyn=self._dyn)
 
 
 def create_fused_optimizer(arena: ParamArena, optim_opts: OptimOpts) -> FusedArenaOptimizer:

@@ -159,12 +159,14 @@ class GradBucketPipeline:
         else:
             self.optimizer.apply_range(lo, hi, grad_scale=self.grad_scale, clip_coef_dev=coef)
 
-    def finish_step(self) -> None:
+    def finish_step(self, defer_tail: bool = False) -> None:
         """Call after ``backward()`` returned: reduces/updates whatever is still outstanding and
-        re-joins the side stream."""
+        re-joins the side stream.  ``defer_tail=True`` (CUDA-graph capture) leaves the tail
+        launches (norm + update of whatever was not updated eagerly) to ``run_tail()``."""
         if not self._step_open:
             raise RuntimeError("finish_step() without begin_step()")
         self._step_open = False
+        self._tail_deferred = False
         if self._ready != self._n_slots:
             missing = [s.index for s in self.arena.slots if id(s.param) not in self._ready_ids]
             if self.distributed:
@@ -188,9 +190,27 @@ class GradBucketPipeline:
             elif self.distributed and not self.eager:
                 for b in self.buckets:
                     b.work.wait()
+            if defer_tail:
+                self._tail_deferred = True
+                return
             if not self.eager:
                 self._tail_update()
         else:
+            if defer_tail:
+                self._tail_deferred = True
+                return
+            self._tail_update()
+        self.optimizer.end_step()
+
+    @property
+    def has_tail(self) -> bool:
+        """True if a step ends with tail launches (not everything is updated eagerly)."""
+        return not self.eager
+
+    def run_tail(self) -> None:
+        """The deferred part of ``finish_step(defer_tail=True)``; also what a CUDA-graph replay
+        of the captured step is followed by."""
+        if self.has_tail:
             self._tail_update()
         self.optimizer.end_step()
 

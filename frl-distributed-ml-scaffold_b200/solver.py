@@ -274,7 +274,8 @@ class Solver:
                               cache=args.cache, local_rank=args.local_rank,
                               node_idx=args.node_idx, node_count=args.node_count,
                               pipeline=pipeline, buffers=buffers, precision=args.precision,
-                              serialize_state=(args.local_rank == 0))
+                              serialize_state=(args.local_rank == 0),
+                              graph_step=os.environ.get("FRL_B200_CUDA_GRAPH", "0") == "1")
         worker.save_every = args.save_every
         scheduler = create_lr_scheduler(run_opts, worker.optimizer,
                                         checkpoint.epoch if checkpoint else -1)

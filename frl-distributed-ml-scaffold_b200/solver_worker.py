@@ -282,7 +282,7 @@ class SolverWorker:
                  pipeline: Optional[GradBucketPipeline] = None,
                  buffers: Optional[BufferBroadcaster] = None,
                  precision: Precision = Precision.FP32,
-                 serialize_state: bool = True) -> None:
+                 serialize_state: bool = True, graph_step: bool = False) -> None:
         self.model = model
         self.criterion = criterion
         self.optimizer = optimizer
@@ -301,6 +301,13 @@ class SolverWorker:
         self._serialize_state = serialize_state
         self._state_wanted = True      # False for epochs whose state the parent will not save
         self.loss_history: List[Tuple[int, Split, np.ndarray]] = []
+        # CUDA-graph replay of the training step (opt-in: the Problem's forward must be
+        # capturable — static shapes, no host syncs)
+        self.graphed = None
+        if graph_step and device.type == "cuda" and not run_opts.debugGrad \
+                and not isinstance(criterion, GradNormWeightedCriterion):
+            from .graph_step import GraphedTrainStep
+            self.graphed = GraphedTrainStep(self)
         self.save_every = 1
         self.optimizer.zero_grad()
         if device.type == "cuda":
@@ -376,6 +383,8 @@ class SolverWorker:
                     with torch.no_grad():
                         if minibatch_idx % amort == 0:
                             sampler_state.compute_metrics()
+                        if self.graphed is not None and training:
+                            output = [o.clone() for o in output]   # static graph buffers
                         sampler_state.append_sample(raw_meta, data, outputs=output, targets=target)
                         if log_freq > 0 and minibatch_idx % log_freq == 0:
                             self._summarize_times(dataset.data_type, timer)
@@ -450,6 +459,14 @@ class SolverWorker:
         debug_grad = (self.run_opts.debugGrad and isinstance(self.model, MultiTaskModel)
                       and minibatch_idx % 10 == 0)
         needs_graph = training or debug_grad or isinstance(self.criterion, GradNormWeightedCriterion)
+
+        if training and self.graphed is not None and not debug_grad:
+            sink = self.criterion._sink
+            captured = self.graphed.ready_for(data, target)
+            if captured is not None:
+                output, total_loss, sub_loss = captured.run(data, target, sink)
+                return output, total_loss, sub_loss, None
+            self.criterion.set_step_sink(sink, self.criterion._nan_flag)
 
         if self.buffers is not None:
             self.buffers.sync()

@@ -56,26 +56,31 @@ int          frl_device_arch(void);
  * Hyper-parameters are doubles (Python floats): derived constants such as 1-beta2 or the
  * Adam bias corrections are formed in double and rounded to fp32 once, exactly as torch does
  * when it hands Python scalars to fp32 tensor ops.
+ *   dyn      optional DEVICE array of per-step scalars that override the by-value arguments,
+ *            so a CUDA graph that captured the launch stays valid while they change:
+ *            SGD / RMSprop: dyn[0] = lr ;  Adam: dyn[0] = -lr/(1-beta1^t), dyn[1] = sqrt(1-beta2^t).
  * Update rules are torch 2.11's (L2-coupled weight decay: g += wd * p first).
  * ---------------------------------------------------------------------------------------- */
 
 /* SGD: buf = first_step ? g : mu*buf + (1-dampening)*g ; p -= lr*buf.   mu == 0: buf may be NULL. */
 int frl_sgd_momentum(float* p, const void* g, float* buf, void* p_lp, int64_t n,
                      double lr, double mu, double dampening, double wd,
-                     double grad_scale, const float* grad_scale_dev,
+                     double grad_scale, const float* grad_scale_dev, const float* dyn,
                      int first_step, int g_dtype, void* stream);
 
 /* Adam (coupled L2, optional amsgrad when vmax != NULL).  `step` is the 1-based step count
  * used for the bias corrections (computed in double on the host side of the call). */
 int frl_adam(float* p, const void* g, float* m, float* v, float* vmax, void* p_lp, int64_t n,
              double lr, double beta1, double beta2, double eps, double wd, int64_t step,
-             double grad_scale, const float* grad_scale_dev, int g_dtype, void* stream);
+             double grad_scale, const float* grad_scale_dev, const float* dyn, int g_dtype,
+             void* stream);
 
 /* RMSprop (not centered): sq = alpha*sq + (1-alpha)*g^2 ; avg = sqrt(sq)+eps ;
  * mu > 0: buf = mu*buf + g/avg ; p -= lr*buf     else: p -= lr*g/avg  (buf may be NULL). */
 int frl_rmsprop(float* p, const void* g, float* sq, float* buf, void* p_lp, int64_t n,
                 double lr, double alpha, double eps, double wd, double mu,
-                double grad_scale, const float* grad_scale_dev, int g_dtype, void* stream);
+                double grad_scale, const float* grad_scale_dev, const float* dyn, int g_dtype,
+             void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3 — global gradient norm for clipping.

@@ -94,7 +94,7 @@ class KernelDouble:
         return grad_scale * (float(grad_scale_dev.item()) if grad_scale_dev is not None else 1.0)
 
     def sgd_momentum(self, p, g, buf, p_lp, n, *, lr, mu, dampening, wd, grad_scale=1.0,
-                     grad_scale_dev=None, first_step=False):
+                     grad_scale_dev=None, first_step=False, dyn=None):
         self.calls.append(("sgd", n))
         np_, nb = sgd_step(self._np(p), self._np(g), self._np(buf), lr=lr, mu=mu,
                            dampening=dampening, wd=wd, first_step=first_step,
@@ -102,7 +102,7 @@ class KernelDouble:
         self._store(p, np_); self._store(buf, nb); self._store(p_lp, np_)
 
     def adam(self, p, g, m, v, vmax, p_lp, n, *, lr, beta1, beta2, eps, wd, step, grad_scale=1.0,
-             grad_scale_dev=None):
+             grad_scale_dev=None, dyn=None):
         self.calls.append(("adam", n))
         np_, nm, nv, nvm = adam_step(self._np(p), self._np(g), self._np(m), self._np(v),
                                      self._np(vmax), lr=lr, beta1=beta1, beta2=beta2, eps=eps,
@@ -112,7 +112,7 @@ class KernelDouble:
         self._store(p_lp, np_)
 
     def rmsprop(self, p, g, sq, buf, p_lp, n, *, lr, alpha, eps, wd, mu, grad_scale=1.0,
-                grad_scale_dev=None):
+                grad_scale_dev=None, dyn=None):
         self.calls.append(("rmsprop", n))
         np_, nsq, nb = rmsprop_step(self._np(p), self._np(g), self._np(sq), self._np(buf), lr=lr,
                                     alpha=alpha, eps=eps, wd=wd, mu=mu,

@@ -178,3 +178,18 @@ def test_multi_gpu_pipeline_matches_oracle(tmp_path):
                           "29533", script], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("DDP_PARITY_OK") == 3
+
+
+@pytest.mark.parametrize("name", ["toy_sgd", "toy_adam_clip", "toy_uncertainty"])
+def test_cuda_graph_replay_matches_reference_solver(ns, golden_dir, name, monkeypatch):
+    """Same parity bar with the step replayed from a CUDA graph (captured after 3 eager steps)."""
+    monkeypatch.setenv("FRL_B200_CUDA_GRAPH", "1")
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    _, worker, problem, save_dir = _solve_and_capture(ns, CONFIGS[name])
+    assert worker.graphed is not None and len(worker.graphed._graphs) == 1
+    rows = np.concatenate([r for _, _, r in worker.loss_history])
+    np.testing.assert_allclose(rows, g["rows"], rtol=1e-5, atol=1e-6)
+    final = torch.load(os.path.join(save_dir, "final_model.pth"), weights_only=False)
+    for i, k in enumerate(list(g["param_names"])):
+        np.testing.assert_allclose(final["state_dict"][k].numpy(), g["param_%02d" % i],
+                                   rtol=2e-4, atol=2e-6)

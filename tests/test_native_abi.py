@@ -42,8 +42,8 @@ def test_abi_version_and_struct_layout():
 
 def test_argument_errors_are_reported_without_a_gpu():
     lib = _native.lib()
-    rc = lib.frl_sgd_momentum(None, None, None, None, 16, 0.1, 0.9, 0.0, 0.0, 1.0, None, 0, 0, None)
+    rc = lib.frl_sgd_momentum(None, None, None, None, 16, 0.1, 0.9, 0.0, 0.0, 1.0, None, None, 0, 0, None)
     assert rc < 0
     assert b"frl_sgd_momentum" in lib.frl_last_error()
-    rc = lib.frl_adam(None, None, None, None, None, None, 16, 0.1, 0.9, 0.999, 1e-8, 0.0, 0, 1.0, None, 0, None)
+    rc = lib.frl_adam(None, None, None, None, None, None, 16, 0.1, 0.9, 0.999, 1e-8, 0.0, 0, 1.0, None, None, 0, None)
     assert rc < 0
