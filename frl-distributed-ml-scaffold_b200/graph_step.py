@@ -17,10 +17,15 @@ What stays outside the graph (cheap, and needs per-step values):
 """
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import gc
+import logging
+
 import torch
 
 from . import _native
 from .types import Precision
+
+logger = logging.getLogger(__name__)
 
 
 def _signature(data: Sequence[torch.Tensor], target) -> Tuple:
@@ -49,7 +54,21 @@ class GraphedTrainStep:
         self._seen[sig] = n + 1
         if n < self.WARMUP_STEPS or self.worker.optimizer._steps < 1:
             return None
-        cap = _Captured(self.worker, data, target)
+        if not self.enabled:
+            return None
+        try:
+            cap = _Captured(self.worker, data, target)
+        except Exception as e:                     # noqa: BLE001
+            # not capturable (host sync in the Problem's forward, a stale autograd graph bound
+            # to another stream, ...): stay on the eager path for the rest of the run
+            logger.warning("CUDA-graph capture of the training step failed (%s); "
+                           "continuing with eager launches", str(e).splitlines()[0])
+            self.enabled = False
+            w = self.worker
+            w.pipeline._step_open = False
+            w.optimizer._in_step = False
+            torch.cuda.synchronize()
+            return None
         self._graphs[sig] = cap
         return cap
 
@@ -70,6 +89,7 @@ class _Captured:
 
         w.optimizer.enable_dynamic_scalars()
         w.criterion.set_step_sink(None, None)
+        gc.collect()                  # free autograd graphs of earlier (eager) steps
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):

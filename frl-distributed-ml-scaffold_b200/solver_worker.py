@@ -393,6 +393,10 @@ class SolverWorker:
                             losses = dict(zip(names, row[1:]))
                             losses["total_loss"] = row[0]
                             logger.info("{}: {}".format(minibatch_idx, json.dumps(losses)))
+                    # drop the autograd graph of this step now: its AccumulateGrad nodes would
+                    # otherwise still be alive (and bound to this stream) when the next step is
+                    # captured into a CUDA graph
+                    output = total_loss = sub_loss = None
                     timer.batch.update(time.time() - batch_start)
                     batch_start = time.time()
 
