@@ -67,6 +67,7 @@ class GraphedTrainStep:
             w = self.worker
             w.pipeline._step_open = False
             w.optimizer._in_step = False
+            w.optimizer._dyn = None
             torch.cuda.synchronize()
             return None
         self._graphs[sig] = cap
