@@ -433,7 +433,18 @@ def main_b200(args, rank, local_rank, world):
                 "clocks": clocks.summary(), "final_loss": float(losses[-1])}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Release the captured graphs (they hold NCCL work) before anything NCCL is torn down,
+        # line the ranks up, and leave without running communicator destructors: a rank that
+        # exits early while another still tears down captured collectives can hang the job.
+        import gc
+        worker.graphed = None
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
