@@ -53,7 +53,11 @@ class ArenaSlot:
 class ParamArena:
     def __init__(self, model_params: Iterable[nn.Parameter],
                  criterion_params: Iterable[nn.Parameter] = (),
-                 *, device: torch.device, precision: Precision = Precision.FP32) -> None:
+                 *, device: torch.device, precision: Precision = Precision.FP32,
+                 shared_allocator=None) -> None:
+        """``shared_allocator(numel, dtype) -> zeroed tensor``: where the vectors other ranks must
+        reach (``grad`` and the weights the modules read) come from — symmetric/multicast memory
+        for the fused NVLS step; default ``torch.zeros``."""
         self.device = torch.device(device)
         self.precision = precision
         self.all_params: List[nn.Parameter] = []
@@ -81,14 +85,22 @@ class ParamArena:
         self.numel = off
         self.grad_dtype = torch.bfloat16 if precision == Precision.BF16 else torch.float32
 
-        self.master = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+        def shared(dtype):
+            if shared_allocator is not None and self.numel > 0:
+                return shared_allocator(self.numel, dtype)
+            return torch.zeros(self.numel, dtype=dtype, device=self.device)
+
+        bf16_mode = precision == Precision.BF16
+        self.master = (torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+                       if bf16_mode else shared(torch.float32))
         with torch.no_grad():
             for s in self.slots:
                 self.master[s.offset:s.end].copy_(s.param.detach().reshape(-1))
         self.lp: Optional[torch.Tensor] = None
-        if precision == Precision.BF16:
-            self.lp = self.master.to(torch.bfloat16)
-        self.grad = torch.zeros(self.numel, dtype=self.grad_dtype, device=self.device)
+        if bf16_mode:
+            self.lp = shared(torch.bfloat16)
+            self.lp.copy_(self.master)
+        self.grad = shared(self.grad_dtype)
         self._by_id: Dict[int, ArenaSlot] = {id(s.param): s for s in self.slots}
         self._repoint()
 

@@ -1,0 +1,238 @@
+// K7 — fused gradient all-reduce + optimizer update + weight broadcast over NVSwitch multicast
+// (NVLS), one kernel per gradient bucket (sm_100a, world_size > 1).
+//
+// The reference step is "DDP all-reduces every bucket, then torch.optim updates every replica"
+// (reference solver.py:287-289 + solver_worker.py:586-592): every GPU receives the full reduced
+// gradient and every GPU streams the full 20-28 B/param optimizer update.  Here each rank owns
+// 1/world of every bucket:
+//
+//   barrier      every rank has finished writing this bucket's gradients
+//   reduce       g = multimem.ld_reduce(add) on the bucket's MULTICAST address: the NVSwitch
+//                sums the world_size copies in flight; only this rank's shard crosses its link
+//   update       torch-exact SGD/Adam/RMSprop on the shard (fp32 master + state, local HBM)
+//   broadcast    multimem.st of the new bf16 shadow weights (BF16 mode) or fp32 weights (FP32
+//                mode) to the multicast address: the switch replicates them into every replica
+//   barrier      all replicas have every shard
+//
+// Per GPU and step this moves S(1 + 1/world) bytes per direction over NVLink (S = gradient
+// bytes) — what an NVLS all-reduce alone moves — and divides the optimizer's HBM traffic and
+// state updates by world_size.  No NCCL call, no separate update launch.
+//
+// Cross-GPU synchronisation uses the symmetric-memory signal pads: block b of rank r raises flag
+// (b, r) in every peer's pad and waits for flag (b, peer) in its own (CAS 0->1 / 1->0), so all
+// ranks must launch the same grid.  Data movement is 16 bytes per multimem instruction.
+#include "frl_common.cuh"
+#include "optim_rules.cuh"
+
+namespace frl {
+
+constexpr int kNThreads = 512;
+constexpr int kNUnroll = 2;
+
+__device__ __forceinline__ void mm_ld_reduce_bf16x8(const void* mc, uint32_t (&r)[4]) {
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(mc) : "memory");
+}
+__device__ __forceinline__ void mm_ld_reduce_f32x4(const void* mc, float (&r)[4]) {
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "l"(mc) : "memory");
+}
+__device__ __forceinline__ void mm_st_b128(void* mc, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(mc), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// All ranks' block `blockIdx.x` meet.  Threads 0..world-1 each handle one peer.
+__device__ __forceinline__ void meet_peers(uint32_t* const* pads, int rank, int world, int base) {
+    __syncthreads();
+    if (threadIdx.x < world) {
+        const int peer = threadIdx.x;
+        uint32_t* put = pads[peer] + base + blockIdx.x * world + rank;
+        uint32_t* wait = pads[rank] + base + blockIdx.x * world + peer;
+        __threadfence_system();                                   // release everything before
+        while (atomicCAS_system(put, 0u, 1u) != 0u) {}
+        while (atomicCAS_system(wait, 1u, 0u) != 1u) {}
+        __threadfence_system();                                   // acquire everything after
+    }
+    __syncthreads();
+}
+
+struct NvlsCommon {
+    uint32_t* const* pads;
+    int rank, world, pad_base;
+    int64_t n;            // bucket elements
+    float gscale;
+    const float* dyn;
+};
+
+// BF16 mode: bf16 gradients in, fp32 master/state local, bf16 shadow multicast out. 8 elems / item.
+template <typename Rule, int NS>
+__global__ void __launch_bounds__(kNThreads)
+nvls_update_bf16(float* __restrict__ p_, float* __restrict__ s0_, float* __restrict__ s1_,
+                 float* __restrict__ s2_, const __nv_bfloat16* mc_g, __nv_bfloat16* mc_lp,
+                 Rule rule, NvlsCommon c) {
+    if (c.dyn) rule.patch(c.dyn);
+    meet_peers(c.pads, c.rank, c.world, c.pad_base);
+    const int64_t per = ((c.n + c.world - 1) / c.world + 7) / 8 * 8;
+    const int64_t lo = static_cast<int64_t>(c.rank) * per;
+    int64_t hi = lo + per;
+    if (hi > c.n) hi = c.n;
+    const int64_t items = hi > lo ? (hi - lo + 7) / 8 : 0;        // arena buckets are multiples of 8
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kNThreads;
+    for (int64_t it0 = static_cast<int64_t>(blockIdx.x) * kNThreads + threadIdx.x; it0 < items;
+         it0 += stride * kNUnroll) {
+        uint32_t g[kNUnroll][4];
+        f32x4 vp[kNUnroll][2], a0[kNUnroll][2], a1[kNUnroll][2], a2[kNUnroll][2];
+        const f32x4 zero{0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < kNUnroll; ++u) {
+            const int64_t it = it0 + u * stride;
+            if (it >= items) break;
+            const int64_t e = lo + it * 8;
+            mm_ld_reduce_bf16x8(mc_g + e, g[u]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                vp[u][h] = ld_stream(reinterpret_cast<const f32x4*>(p_ + e) + h);
+                a0[u][h] = NS > 0 ? ld_stream(reinterpret_cast<const f32x4*>(s0_ + e) + h) : zero;
+                a1[u][h] = NS > 1 ? ld_stream(reinterpret_cast<const f32x4*>(s1_ + e) + h) : zero;
+                a2[u][h] = NS > 2 ? ld_stream(reinterpret_cast<const f32x4*>(s2_ + e) + h) : zero;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kNUnroll; ++u) {
+            const int64_t it = it0 + u * stride;
+            if (it >= items) break;
+            const int64_t e = lo + it * 8;
+            const float gs = c.gscale;
+            f32x4 g0{bf16lo(g[u][0]) * gs, bf16hi(g[u][0]) * gs, bf16lo(g[u][1]) * gs, bf16hi(g[u][1]) * gs};
+            f32x4 g1{bf16lo(g[u][2]) * gs, bf16hi(g[u][2]) * gs, bf16lo(g[u][3]) * gs, bf16hi(g[u][3]) * gs};
+            rule(vp[u][0].x, g0.x, a0[u][0].x, a1[u][0].x, a2[u][0].x);
+            rule(vp[u][0].y, g0.y, a0[u][0].y, a1[u][0].y, a2[u][0].y);
+            rule(vp[u][0].z, g0.z, a0[u][0].z, a1[u][0].z, a2[u][0].z);
+            rule(vp[u][0].w, g0.w, a0[u][0].w, a1[u][0].w, a2[u][0].w);
+            rule(vp[u][1].x, g1.x, a0[u][1].x, a1[u][1].x, a2[u][1].x);
+            rule(vp[u][1].y, g1.y, a0[u][1].y, a1[u][1].y, a2[u][1].y);
+            rule(vp[u][1].z, g1.z, a0[u][1].z, a1[u][1].z, a2[u][1].z);
+            rule(vp[u][1].w, g1.w, a0[u][1].w, a1[u][1].w, a2[u][1].w);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                st_stream(reinterpret_cast<f32x4*>(p_ + e) + h, vp[u][h]);
+                if (NS > 0) st_stream(reinterpret_cast<f32x4*>(s0_ + e) + h, a0[u][h]);
+                if (NS > 1) st_stream(reinterpret_cast<f32x4*>(s1_ + e) + h, a1[u][h]);
+                if (NS > 2) st_stream(reinterpret_cast<f32x4*>(s2_ + e) + h, a2[u][h]);
+            }
+            mm_st_b128(mc_lp + e, pack_bf16(vp[u][0].x, vp[u][0].y), pack_bf16(vp[u][0].z, vp[u][0].w),
+                       pack_bf16(vp[u][1].x, vp[u][1].y), pack_bf16(vp[u][1].z, vp[u][1].w));
+        }
+    }
+    meet_peers(c.pads, c.rank, c.world, c.pad_base);
+}
+
+// FP32 mode: fp32 gradients in, parameters ARE the master: multicast the new fp32 weights.
+template <typename Rule, int NS>
+__global__ void __launch_bounds__(kNThreads)
+nvls_update_f32(const float* __restrict__ p_, float* __restrict__ s0_, float* __restrict__ s1_,
+                float* __restrict__ s2_, const float* mc_g, float* mc_p, Rule rule, NvlsCommon c) {
+    if (c.dyn) rule.patch(c.dyn);
+    meet_peers(c.pads, c.rank, c.world, c.pad_base);
+    const int64_t per = ((c.n + c.world - 1) / c.world + 7) / 8 * 8;
+    const int64_t lo = static_cast<int64_t>(c.rank) * per;
+    int64_t hi = lo + per;
+    if (hi > c.n) hi = c.n;
+    const int64_t items = hi > lo ? (hi - lo + 3) / 4 : 0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kNThreads;
+    for (int64_t it = static_cast<int64_t>(blockIdx.x) * kNThreads + threadIdx.x; it < items; it += stride) {
+        const int64_t e = lo + it * 4;
+        float g[4];
+        mm_ld_reduce_f32x4(mc_g + e, g);
+        f32x4 vp = ld_stream(reinterpret_cast<const f32x4*>(p_ + e));
+        const f32x4 zero{0.f, 0.f, 0.f, 0.f};
+        f32x4 a0 = NS > 0 ? ld_stream(reinterpret_cast<const f32x4*>(s0_ + e)) : zero;
+        f32x4 a1 = NS > 1 ? ld_stream(reinterpret_cast<const f32x4*>(s1_ + e)) : zero;
+        f32x4 a2 = NS > 2 ? ld_stream(reinterpret_cast<const f32x4*>(s2_ + e)) : zero;
+        const float gs = c.gscale;
+        rule(vp.x, g[0] * gs, a0.x, a1.x, a2.x);
+        rule(vp.y, g[1] * gs, a0.y, a1.y, a2.y);
+        rule(vp.z, g[2] * gs, a0.z, a1.z, a2.z);
+        rule(vp.w, g[3] * gs, a0.w, a1.w, a2.w);
+        if (NS > 0) st_stream(reinterpret_cast<f32x4*>(s0_ + e), a0);
+        if (NS > 1) st_stream(reinterpret_cast<f32x4*>(s1_ + e), a1);
+        if (NS > 2) st_stream(reinterpret_cast<f32x4*>(s2_ + e), a2);
+        mm_st_b128(mc_p + e, __float_as_uint(vp.x), __float_as_uint(vp.y), __float_as_uint(vp.z),
+                   __float_as_uint(vp.w));
+    }
+    meet_peers(c.pads, c.rank, c.world, c.pad_base);
+}
+
+template <typename Rule, int NS>
+static int launch_nvls(const Rule& rule, float* p, float* s0, float* s1, float* s2, const void* mc_g,
+                       void* mc_out, int64_t n, int rank, int world, void* const* pads, int pad_base,
+                       int max_blocks, double gscale, const float* dyn, int g_dtype, void* stream,
+                       const char* name) {
+    FRL_REQUIRE(p && mc_g && mc_out && pads, FRL_E_ARG, "%s: null pointer", name);
+    FRL_REQUIRE(world >= 2 && world <= 32 && rank >= 0 && rank < world, FRL_E_ARG, "%s: rank/world", name);
+    FRL_REQUIRE(n >= 0 && n % 8 == 0, FRL_E_ARG, "%s: bucket size must be a multiple of 8 elements", name);
+    FRL_REQUIRE(g_dtype == FRL_F32 || g_dtype == FRL_BF16, FRL_E_DTYPE, "%s: g_dtype", name);
+    FRL_REQUIRE(aligned16(p) && aligned16(s0) && aligned16(s1) && aligned16(s2) && aligned16(mc_g) &&
+                aligned16(mc_out), FRL_E_ALIGN, "%s: 16-byte alignment", name);
+    FRL_REQUIRE(max_blocks >= 1 && max_blocks <= 64, FRL_E_ARG, "%s: max_blocks in 1..64", name);
+    NvlsCommon c{reinterpret_cast<uint32_t* const*>(pads), rank, world, pad_base, n,
+                 static_cast<float>(gscale), dyn};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the grid must be identical on every rank: it depends on arguments only
+    if (g_dtype == FRL_BF16)
+        nvls_update_bf16<Rule, NS><<<max_blocks, kNThreads, 0, st>>>(
+            p, s0, s1, s2, static_cast<const __nv_bfloat16*>(mc_g), static_cast<__nv_bfloat16*>(mc_out), rule, c);
+    else
+        nvls_update_f32<Rule, NS><<<max_blocks, kNThreads, 0, st>>>(
+            p, s0, s1, s2, static_cast<const float*>(mc_g), static_cast<float*>(mc_out), rule, c);
+    return after_launch(name);
+}
+
+}  // namespace frl
+
+using namespace frl;
+
+extern "C" int frl_nvls_sgd(float* p, float* buf, const void* mc_g, void* mc_out, int64_t n, int rank,
+                            int world, void* const* signal_pads_dev, int pad_base, int max_blocks,
+                            double lr, double mu, double dampening, double wd, double grad_scale,
+                            const float* dyn, int first_step, int g_dtype, void* stream) {
+    FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_nvls_sgd: momentum needs buf");
+    const SgdRule r = make_sgd_rule(lr, mu, dampening, wd, first_step);
+    if (mu != 0.0)
+        return launch_nvls<SgdRule, 1>(r, p, buf, nullptr, nullptr, mc_g, mc_out, n, rank, world,
+                                       signal_pads_dev, pad_base, max_blocks, grad_scale, dyn, g_dtype,
+                                       stream, "frl_nvls_sgd");
+    return launch_nvls<SgdRule, 0>(r, p, nullptr, nullptr, nullptr, mc_g, mc_out, n, rank, world,
+                                   signal_pads_dev, pad_base, max_blocks, grad_scale, dyn, g_dtype, stream,
+                                   "frl_nvls_sgd");
+}
+
+extern "C" int frl_nvls_adam(float* p, float* m, float* v, float* vmax, const void* mc_g, void* mc_out,
+                             int64_t n, int rank, int world, void* const* signal_pads_dev, int pad_base,
+                             int max_blocks, double lr, double beta1, double beta2, double eps, double wd,
+                             int64_t step, double grad_scale, const float* dyn, int g_dtype, void* stream) {
+    FRL_REQUIRE(m && v && step >= 1, FRL_E_ARG, "frl_nvls_adam: state/step");
+    if (vmax)
+        return launch_nvls<AdamRule<true>, 3>(make_adam_rule<true>(lr, beta1, beta2, eps, wd, step), p, m, v,
+                                              vmax, mc_g, mc_out, n, rank, world, signal_pads_dev, pad_base,
+                                              max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_adam");
+    return launch_nvls<AdamRule<false>, 2>(make_adam_rule<false>(lr, beta1, beta2, eps, wd, step), p, m, v,
+                                           nullptr, mc_g, mc_out, n, rank, world, signal_pads_dev, pad_base,
+                                           max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_adam");
+}
+
+extern "C" int frl_nvls_rmsprop(float* p, float* sq, float* buf, const void* mc_g, void* mc_out, int64_t n,
+                                int rank, int world, void* const* signal_pads_dev, int pad_base,
+                                int max_blocks, double lr, double alpha, double eps, double wd, double mu,
+                                double grad_scale, const float* dyn, int g_dtype, void* stream) {
+    FRL_REQUIRE(sq, FRL_E_ARG, "frl_nvls_rmsprop: null sq");
+    FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_nvls_rmsprop: momentum needs buf");
+    if (mu != 0.0)
+        return launch_nvls<RmspropRule<true>, 2>(make_rmsprop_rule<true>(lr, alpha, eps, wd, mu), p, sq, buf,
+                                                 nullptr, mc_g, mc_out, n, rank, world, signal_pads_dev, pad_base,
+                                                 max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_rmsprop");
+    return launch_nvls<RmspropRule<false>, 1>(make_rmsprop_rule<false>(lr, alpha, eps, wd, mu), p, sq, nullptr,
+                                              nullptr, mc_g, mc_out, n, rank, world, signal_pads_dev, pad_base,
+                                              max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_rmsprop");
+}

@@ -14,66 +14,13 @@
 // before the first use (UNROLL * (2 + NSTATE) independent 128-bit loads in flight), which is
 // what keeps ~100 KB per SM outstanding — the amount Little's law asks for at ~6.5 TB/s.
 #include "frl_common.cuh"
+#include "optim_rules.cuh"
 
 namespace frl {
 
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
 constexpr int kTileVec = kThreads * kUnroll;   // vec4 items per tile
-
-// ---- update rules (scalar, fp32) ------------------------------------------------------------
-struct SgdRule {
-    float neg_lr, mu, one_minus_damp, wd;
-    int first_step, has_buf;
-    static constexpr int kStates = 1;
-    __device__ __forceinline__ void patch(const float* dyn) { neg_lr = -__ldg(dyn); }
-    __device__ __forceinline__ void operator()(float& p, float g, float& buf, float&, float&) const {
-        g = fmaf(wd, p, g);
-        if (has_buf) {
-            buf = first_step ? g : fmaf(mu, buf, one_minus_damp * g);
-            g = buf;
-        }
-        p = fmaf(neg_lr, g, p);
-    }
-};
-
-template <bool AMSGRAD>
-struct AdamRule {
-    float w1;               // 1 - beta1   (lerp weight)
-    float beta2, w2;        // beta2, 1 - beta2
-    float eps, wd;
-    float neg_step_size;    // -lr / (1 - beta1^t)
-    float bc2_sqrt;         // sqrt(1 - beta2^t)
-    static constexpr int kStates = AMSGRAD ? 3 : 2;
-    __device__ __forceinline__ void patch(const float* dyn) {
-        neg_step_size = __ldg(dyn);
-        bc2_sqrt = __ldg(dyn + 1);
-    }
-    __device__ __forceinline__ void operator()(float& p, float g, float& m, float& v, float& vmax) const {
-        g = fmaf(wd, p, g);
-        m = fmaf(w1, g - m, m);                       // exp_avg.lerp_(g, 1-beta1), weight < 0.5 branch
-        v = fmaf(w2 * g, g, v * beta2);               // mul_(beta2).addcmul_(g, g, 1-beta2)
-        float vv = v;
-        if (AMSGRAD) { vmax = fmaxf(vmax, v); vv = vmax; }
-        const float denom = sqrtf(vv) / bc2_sqrt + eps;
-        p = fmaf(neg_step_size, m / denom, p);        // addcdiv_(m, denom, -step_size)
-    }
-};
-
-template <bool MOMENTUM>
-struct RmspropRule {
-    float alpha, one_minus_alpha, eps, wd, mu, neg_lr;
-    static constexpr int kStates = MOMENTUM ? 2 : 1;
-    __device__ __forceinline__ void patch(const float* dyn) { neg_lr = -__ldg(dyn); }
-    __device__ __forceinline__ void operator()(float& p, float g, float& sq, float& buf, float&) const {
-        g = fmaf(wd, p, g);
-        sq = fmaf(one_minus_alpha * g, g, sq * alpha);
-        const float avg = sqrtf(sq) + eps;
-        float upd = g / avg;
-        if (MOMENTUM) { buf = fmaf(mu, buf, upd); upd = buf; }
-        p = fmaf(neg_lr, upd, p);
-    }
-};
 
 // ---- gradient vector load (scaled, as fp32) ---------------------------------------------------
 __device__ __forceinline__ f32x4 load_grad4(const f32x4* g, int64_t i) { return ld_stream_ro(g + i); }

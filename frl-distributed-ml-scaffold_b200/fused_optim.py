@@ -36,6 +36,9 @@ class FusedArenaOptimizer(torch.optim.Optimizer):
         # replayed from a CUDA graph, where by-value kernel arguments are frozen at capture
         self._dyn: Optional[torch.Tensor] = None
         self._dyn_last: Optional[Tuple[float, ...]] = None
+        # fused NVLS step (world > 1): set by the pipeline; each rank then updates only its
+        # 1/world shard of every bucket (master + state), the weights arrive by multicast
+        self.nvls = None
 
     # -- device-resident scalars -----------------------------------------------------------------
     def _dyn_values(self) -> Tuple[float, ...]:
@@ -96,6 +99,27 @@ class FusedArenaOptimizer(torch.optim.Optimizer):
 
     def _launch(self, lo: int, hi: int, grad_scale: float, coef) -> None:
         raise NotImplementedError
+
+    # -- fused all-reduce + update + broadcast (K7) ------------------------------------------------
+    def apply_range_nvls(self, lo: int, hi: int, *, grad_scale: float) -> None:
+        if hi > lo:
+            self._launch_nvls(lo, hi, grad_scale)
+
+    def _launch_nvls(self, lo: int, hi: int, grad_scale: float) -> None:
+        raise NotImplementedError
+
+    def _nvls_ptrs(self, lo: int):
+        k = self.nvls
+        return k.mc_grad + lo * k.grad_esz, k.mc_out + lo * k.out_esz
+
+    def shard_of(self, lo: int, hi: int) -> Tuple[int, int]:
+        """Element range of bucket ``[lo, hi)`` this rank owns under the fused NVLS step (same
+        formula as csrc/nvls.cu)."""
+        k = self.nvls
+        n = hi - lo
+        per = ((n + k.world - 1) // k.world + 7) // 8 * 8
+        a = min(lo + k.rank * per, hi)
+        return a, min(a + per, hi)
 
     @torch.no_grad()
     def step(self, closure=None, *, grad_scale: float = 1.0,
@@ -182,6 +206,17 @@ class FusedSGD(FusedArenaOptimizer):
                              grad_scale=grad_scale, grad_scale_dev=coef,
                              first_step=(self._steps == 0), dyn=self._dyn)
 
+    def _launch_nvls(self, lo, hi, grad_scale):
+        h = self.hyper
+        mu = float(h["momentum"])
+        mc_g, mc_out = self._nvls_ptrs(lo)
+        buf = self._state("momentum_buffer")[lo:hi] if mu != 0.0 else None
+        KERNELS.nvls_sgd(self.arena.master[lo:hi], buf, mc_g, mc_out, hi - lo, self.nvls,
+                         lr=float(h["lr"]), mu=mu, dampening=float(h["dampening"]),
+                         wd=float(h["weight_decay"]), grad_scale=grad_scale,
+                         first_step=(self._steps == 0),
+                         g_dtype=KERNELS.dtype_code(self.arena.grad.dtype), dyn=self._dyn)
+
 
 class FusedAdam(FusedArenaOptimizer):
     STATE_NAMES = (("exp_avg", "exp_avg"), ("exp_avg_sq", "exp_avg_sq"),
@@ -213,6 +248,17 @@ class FusedAdam(FusedArenaOptimizer):
                      wd=float(h["weight_decay"]), step=self._steps + 1,
                      grad_scale=grad_scale, grad_scale_dev=coef, dyn=self._dyn)
 
+    def _launch_nvls(self, lo, hi, grad_scale):
+        h = self.hyper
+        mc_g, mc_out = self._nvls_ptrs(lo)
+        vmax = self._state("max_exp_avg_sq")[lo:hi] if h["amsgrad"] else None
+        KERNELS.nvls_adam(self.arena.master[lo:hi], self._state("exp_avg")[lo:hi],
+                          self._state("exp_avg_sq")[lo:hi], vmax, mc_g, mc_out, hi - lo, self.nvls,
+                          lr=float(h["lr"]), beta1=float(h["betas"][0]), beta2=float(h["betas"][1]),
+                          eps=float(h["eps"]), wd=float(h["weight_decay"]), step=self._steps + 1,
+                          grad_scale=grad_scale, g_dtype=KERNELS.dtype_code(self.arena.grad.dtype),
+                          dyn=self._dyn)
+
 
 class FusedRMSprop(FusedArenaOptimizer):
     STATE_NAMES = (("square_avg", "square_avg"), ("momentum_buffer", "momentum_buffer"))
@@ -234,6 +280,17 @@ class FusedRMSprop(FusedArenaOptimizer):
                         lr=float(h["lr"]), alpha=float(h["alpha"]), eps=float(h["eps"]),
                         wd=float(h["weight_decay"]), mu=mu, grad_scale=grad_scale,
                         grad_scale_dev=coef, dyn=self._dyn)
+
+    def _launch_nvls(self, lo, hi, grad_scale):
+        h = self.hyper
+        mu = float(h["momentum"])
+        mc_g, mc_out = self._nvls_ptrs(lo)
+        buf = self._state("momentum_buffer")[lo:hi] if mu != 0.0 else None
+        KERNELS.nvls_rmsprop(self.arena.master[lo:hi], self._state("square_avg")[lo:hi], buf, mc_g,
+                             mc_out, hi - lo, self.nvls, lr=float(h["lr"]), alpha=float(h["alpha"]),
+                             eps=float(h["eps"]), wd=float(h["weight_decay"]), mu=mu,
+                             grad_scale=grad_scale,
+                             g_dtype=KERNELS.dtype_code(self.arena.grad.dtype), dyn=self._dyn)
 
 
 def create_fused_optimizer(arena: ParamArena, optim_opts: OptimOpts) -> FusedArenaOptimizer:

@@ -28,7 +28,7 @@ KERNELS = _native     # swapped by CPU tests of the host logic
 
 
 class _Bucket:
-    __slots__ = ("lo", "hi", "slots", "pending", "work", "launched")
+    __slots__ = ("lo", "hi", "slots", "pending", "work", "launched", "replicated")
 
     def __init__(self, lo: int, hi: int):
         self.lo, self.hi = lo, hi
@@ -36,13 +36,14 @@ class _Bucket:
         self.pending = 0
         self.work = None
         self.launched = False
+        self.replicated = False      # fused-NVLS runs: this bucket keeps the NCCL + K2 path
 
 
 class GradBucketPipeline:
     def __init__(self, arena: ParamArena, optimizer: FusedArenaOptimizer, *,
                  process_group=None, world_size: int = 1, clip_norm: float = 0.0,
                  bucket_cap_mb: float = 25.0, first_bucket_mb: Optional[float] = 1.0,
-                 eager_update: bool = True) -> None:
+                 eager_update: bool = True, nvls_link=None) -> None:
         self.arena = arena
         self.optimizer = optimizer
         self.pg = process_group
@@ -60,7 +61,19 @@ class GradBucketPipeline:
         cap = int(bucket_cap_mb * 1024 * 1024)
         first = int(first_bucket_mb * 1024 * 1024) if (first_bucket_mb and self.distributed) else None
         ranges = arena.buckets(cap, first) if (self.distributed or self.eager) else [(0, arena.numel)]
+        use_nvls = nvls_link is not None and self.distributed and self.eager
+        if use_nvls and arena.lp is not None and arena.model_end < arena.numel:
+            # BF16 mode: criterion parameters read the fp32 master, which the fused NVLS step keeps
+            # current only on the owning rank -> give them their own, replicated (NCCL) bucket
+            cut = arena.model_end
+            split = []
+            for lo, hi in ranges:
+                split += [(cut, hi), (lo, cut)] if lo < cut < hi else [(lo, hi)]
+            ranges = split
         self.buckets: List[_Bucket] = [_Bucket(lo, hi) for lo, hi in ranges]
+        if use_nvls and arena.lp is not None:
+            for b in self.buckets:
+                b.replicated = b.lo >= arena.model_end
         self._bucket_of = {}
         for s in arena.slots:
             for b in self.buckets:
@@ -82,6 +95,11 @@ class GradBucketPipeline:
             self.clip_out = torch.zeros(3, dtype=torch.float32, device=arena.device)
             nbytes = KERNELS.reduce_scratch_bytes()
             self.clip_scratch = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=arena.device)
+        # fused NVLS step: all-reduce + update + weight broadcast are ONE kernel per bucket
+        # (csrc/nvls.cu); needs per-bucket updates, so clipping keeps the NCCL + K2/K3 path
+        self.nvls = nvls_link if use_nvls else None
+        if self.nvls is not None:
+            optimizer.nvls = self.nvls
         self._step_open = False
         self.step_id = 0
         self.linear_sites = []
@@ -136,28 +154,38 @@ class GradBucketPipeline:
             self.side_stream.wait_stream(cur)
             torch.cuda.set_stream(self.side_stream)
         try:
-            if self.distributed:
+            if self.nvls is not None and not b.replicated:
+                self._update(b.lo, b.hi, None)        # K7: reduce + update + broadcast
+            elif self.distributed:
                 b.work = dist.all_reduce(self.arena.grad[b.lo:b.hi], op=dist.ReduceOp.SUM,
                                          group=self.pg, async_op=True)
                 if self.eager:
                     b.work.wait()             # stream-level wait, the host does not block
-            if self.eager:
+                    self._update(b.lo, b.hi, None)
+            elif self.eager:
                 self._update(b.lo, b.hi, None)
         finally:
             if self.on_cuda:
                 torch.cuda.set_stream(cur)
         b.launched = True
 
+    def _apply(self, lo: int, hi: int, coef) -> None:
+        if self.nvls is not None and lo < self.arena.model_end or \
+                (self.nvls is not None and self.arena.lp is None):
+            self.optimizer.apply_range_nvls(lo, hi, grad_scale=self.grad_scale)
+        else:
+            self.optimizer.apply_range(lo, hi, grad_scale=self.grad_scale, clip_coef_dev=coef)
+
     def _update(self, lo: int, hi: int, coef) -> None:
         if self.record_update_events and self.on_cuda:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            self.optimizer.apply_range(lo, hi, grad_scale=self.grad_scale, clip_coef_dev=coef)
+            self._apply(lo, hi, coef)
             e1.record()
             self.update_events.append((e0, e1, lo, hi))
         else:
-            self.optimizer.apply_range(lo, hi, grad_scale=self.grad_scale, clip_coef_dev=coef)
+            self._apply(lo, hi, coef)
 
     def finish_step(self, defer_tail: bool = False) -> None:
         """Call after ``backward()`` returned: reduces/updates whatever is still outstanding and
@@ -261,6 +289,27 @@ class GradBucketPipeline:
             return
         dist.broadcast(self.arena.master, src=src, group=self.pg)
         self.arena.refresh_shadow()
+
+    def sync_sharded_state(self) -> None:
+        """Fused NVLS step only: every rank holds the current fp32 master / optimizer state of its
+        own shards; before a checkpoint export make them whole everywhere (collective call)."""
+        if self.nvls is None:
+            return
+        opt = self.optimizer
+        vecs = list(opt._vec.values())
+        if self.arena.lp is not None:
+            vecs.append(self.arena.master)         # FP32 mode multicasts the master itself
+        for vec in vecs:
+            whole = torch.zeros_like(vec)
+            for b in self.buckets:
+                if b.replicated:
+                    if self.nvls.rank == 0:
+                        whole[b.lo:b.hi] = vec[b.lo:b.hi]
+                    continue
+                a, z = opt.shard_of(b.lo, b.hi)
+                whole[a:z] = vec[a:z]
+            dist.all_reduce(whole, op=dist.ReduceOp.SUM, group=self.pg)
+            vec.copy_(whole)
 
     def remove_hooks(self) -> None:
         for h in self._handles:

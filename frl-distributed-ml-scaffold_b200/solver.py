@@ -245,8 +245,14 @@ class Solver:
         if distributed:
             cls._init_process_group(args, device)
 
+        # world > 1 without clipping: arena vectors other ranks reach go to symmetric/multicast
+        # memory so all-reduce + update + broadcast can be one NVLS kernel per bucket
+        symm_alloc = None
+        if distributed and not run_opts.optim.gradientClip:
+            from .symm import try_make_allocator
+            symm_alloc = try_make_allocator(device, args.world_size)
         arena = ParamArena(model.parameters(), criterion.parameters(), device=device,
-                           precision=args.precision)
+                           precision=args.precision, shared_allocator=symm_alloc)
         if args.precision == Precision.BF16:
             for buf in model.buffers():
                 if buf.is_floating_point():
@@ -254,8 +260,15 @@ class Solver:
         optimizer = create_fused_optimizer(arena, run_opts.optim)
         if checkpoint:
             optimizer.load_state_dict(checkpoint.optimizerState)
+        nvls_link = None
+        if symm_alloc is not None:
+            from .symm import make_link
+            nvls_link = make_link(symm_alloc, arena.grad,
+                                  arena.lp if arena.lp is not None else arena.master,
+                                  max_blocks=int(os.environ.get("FRL_B200_NVLS_BLOCKS", "32")))
         pipeline = GradBucketPipeline(
             arena, optimizer, world_size=args.world_size, clip_norm=run_opts.optim.gradientClip,
+            nvls_link=nvls_link,
             bucket_cap_mb=float(os.environ.get("FRL_B200_BUCKET_MB", "48")), first_bucket_mb=None,
             eager_update=os.environ.get("FRL_B200_EAGER_UPDATE",
                                         "1" if args.world_size > 1 else "0") != "0")

@@ -564,6 +564,8 @@ class SolverWorker:
         the master weights for the duration of the pickle."""
         model_bytes = b""
         optim_bytes = b""
+        if self._state_wanted:
+            self.pipeline.sync_sharded_state()        # collective; no-op unless fused NVLS step
         if self._serialize_state and self._state_wanted:
             was_training = self.model.training
             self.model.eval()

@@ -168,6 +168,37 @@ int64_t frl_colsum_scratch_bytes(int64_t rows, int64_t cols);
 int frl_colsum(const void* x, int x_dtype, int64_t rows, int64_t cols, void* out, int out_dtype,
                int accumulate, void* scratch, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K7 — fused gradient all-reduce + optimizer update + weight broadcast over NVSwitch multicast
+ * (world_size > 1).  Replaces, per gradient bucket, the DDP reducer's ncclAllReduce
+ * (reference solver.py:287-289, run inside solver_worker.py:586) AND optimizer.step()
+ * (solver_worker.py:592) with one kernel: barrier | g = multimem.ld_reduce over all ranks'
+ * bucket copies | update this rank's 1/world shard | multimem.st the new weights into every
+ * replica | barrier.
+ *
+ *   p, state...        LOCAL fp32 master / optimizer-state slices of the bucket [n]
+ *   mc_g               MULTICAST address of the bucket's gradient slice (symmetric allocation)
+ *   mc_out             MULTICAST address of the slice every rank's module reads its weights
+ *                      from: bf16 shadow weights (g_dtype FRL_BF16) or the fp32 master
+ *                      (g_dtype FRL_F32, where p is that same memory, locally addressed)
+ *   signal_pads_dev    device array [world] of pointers to each rank's uint32 signal pad;
+ *                      slots [pad_base, pad_base + max_blocks*world) are used
+ *   max_blocks         grid size; MUST be the same on every rank (1..64)
+ * n must be a multiple of 8; launch order must be identical on all ranks.
+ * ---------------------------------------------------------------------------------------- */
+int frl_nvls_sgd(float* p, float* buf, const void* mc_g, void* mc_out, int64_t n, int rank,
+                 int world, void* const* signal_pads_dev, int pad_base, int max_blocks,
+                 double lr, double mu, double dampening, double wd, double grad_scale,
+                 const float* dyn, int first_step, int g_dtype, void* stream);
+int frl_nvls_adam(float* p, float* m, float* v, float* vmax, const void* mc_g, void* mc_out,
+                  int64_t n, int rank, int world, void* const* signal_pads_dev, int pad_base,
+                  int max_blocks, double lr, double beta1, double beta2, double eps, double wd,
+                  int64_t step, double grad_scale, const float* dyn, int g_dtype, void* stream);
+int frl_nvls_rmsprop(float* p, float* sq, float* buf, const void* mc_g, void* mc_out, int64_t n,
+                     int rank, int world, void* const* signal_pads_dev, int pad_base,
+                     int max_blocks, double lr, double alpha, double eps, double wd, double mu,
+                     double grad_scale, const float* dyn, int g_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,15 +30,26 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = False
     ns = synthetic.api_namespace("frl_b200")
-    for algo, clip in (("sgd", 0.0), ("adam", 0.0), ("sgd", 0.05)):
+    from frl_b200.symm import make_link, try_make_allocator
+    alloc = try_make_allocator(dev, world)
+    if rank == 0:
+        print("NVLS_AVAILABLE", alloc is not None, flush=True)
+    combos = [("sgd", 0.0, False), ("adam", 0.0, False), ("sgd", 0.05, False)]
+    if alloc is not None:
+        combos += [("sgd", 0.0, True), ("adam", 0.0, True), ("rmsprop", 0.0, True)]
+    for algo, clip, nvls in combos:
         torch.manual_seed(123 + rank)                 # different init per rank: broadcast must fix
         problem = synthetic.make_toy_problem(ns, "/tmp/unused")
         model = problem.get_model().to(dev)
         crit = problem.get_criterion().to(dev)
-        arena = ParamArena(model.parameters(), crit.parameters(), device=dev)
-        opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm(algo), lr=0.02))
+        arena = ParamArena(model.parameters(), crit.parameters(), device=dev,
+                           shared_allocator=alloc if nvls else None)
+        lr = 0.002 if algo == "rmsprop" else 0.02
+        opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm(algo), lr=lr))
+        link = make_link(alloc, arena.grad, arena.master, max_blocks=8) if nvls else None
         pipe = grad_sync.GradBucketPipeline(arena, opt, world_size=world, clip_norm=clip,
-                                            bucket_cap_mb=0.02, first_bucket_mb=0.005)
+                                            bucket_cap_mb=0.02, first_bucket_mb=0.005, nvls_link=link)
+        assert (pipe.nvls is not None) == nvls
         pipe.broadcast_parameters(0)
         assert len(pipe.buckets) >= 3
         g = torch.Generator().manual_seed(7)
@@ -64,7 +75,7 @@ def main():
             ref_problem = synthetic.make_toy_problem(ns, "/tmp/unused")
             ref = ref_problem.get_model()
             rc = ref_problem.get_criterion()
-            ropt = ref_loop.make_optimizer(ref.parameters(), ref_loop.OptimSpec(algo=algo, lr=0.02))
+            ropt = ref_loop.make_optimizer(ref.parameters(), ref_loop.OptimSpec(algo=algo, lr=lr))
             ref.train()
             for x, yr, yc in batches:
                 out = ref([x])
@@ -77,9 +88,20 @@ def main():
                 ropt.step()
             want = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
             # Adam's m/(sqrt(v)+eps) amplifies fp32 rounding where v is tiny; a step moves a weight by ~lr
-            tol = dict(rtol=1e-3, atol=5e-5) if algo == "adam" else dict(rtol=2e-4, atol=2e-6)
+            tol = dict(rtol=1e-3, atol=5e-5) if algo != "sgd" else dict(rtol=2e-4, atol=2e-6)
             np.testing.assert_allclose(mine.cpu().numpy(), want.numpy(), **tol)
-            print("DDP_PARITY_OK", algo, clip, "world", world, flush=True)
+        if nvls:
+            # sharded optimizer state becomes whole again on every rank (collective)
+            pipe.sync_sharded_state()
+            if rank == 0:
+                name = {"sgd": "momentum_buffer", "adam": "exp_avg", "rmsprop": "square_avg"}[algo]
+                got = opt.state_dict()["state"]
+                want_state = ropt.state_dict()["state"]
+                for k in want_state:
+                    np.testing.assert_allclose(got[k][name].cpu().numpy(), want_state[k][name].numpy(),
+                                               rtol=2e-3, atol=1e-5)
+        if rank == 0:
+            print("DDP_PARITY_OK", algo, clip, "nvls" if nvls else "nccl", "world", world, flush=True)
         pipe.remove_hooks()
         dist.barrier()
     dist.destroy_process_group()
