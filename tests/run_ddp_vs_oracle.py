@@ -88,7 +88,10 @@ def main():
                 ropt.step()
             want = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
             # Adam's m/(sqrt(v)+eps) amplifies fp32 rounding where v is tiny; a step moves a weight by ~lr
-            tol = dict(rtol=1e-3, atol=5e-5) if algo != "sgd" else dict(rtol=2e-4, atol=2e-6)
+            # Adam / RMSprop divide by sqrt(v)+eps: where v is tiny fp32 rounding is amplified; one
+            # step moves a weight by ~lr (Adam) or ~10*lr (RMSprop with momentum)
+            tol = {"sgd": dict(rtol=2e-4, atol=2e-6), "adam": dict(rtol=1e-3, atol=5e-5),
+                   "rmsprop": dict(rtol=2e-3, atol=3e-4)}[algo]
             np.testing.assert_allclose(mine.cpu().numpy(), want.numpy(), **tol)
         if nvls:
             # sharded optimizer state becomes whole again on every rank (collective)
