@@ -58,10 +58,10 @@ SIGNATURES = {
     "frl_cast_scale": (_i, [_vp, _i, _vp, _i, _i64, _f, _vp]),
     "frl_colsum_scratch_bytes": (_i64, [_i64, _i64]),
     "frl_colsum": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i, _vp, _vp]),
-    "frl_nvls_sgd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _i, _d, _d, _d, _d, _d, _vp, _i, _i, _vp]),
-    "frl_nvls_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _i, _d, _d, _d, _d, _d,
+    "frl_nvls_sgd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d, _vp, _i, _i, _vp]),
+    "frl_nvls_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d,
                            _i64, _d, _vp, _i, _vp]),
-    "frl_nvls_rmsprop": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _i, _d, _d, _d, _d, _d, _d,
+    "frl_nvls_rmsprop": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d, _d,
                               _vp, _i, _vp]),
 }
 
@@ -231,7 +231,7 @@ def colsum(x, out, accumulate: bool = False) -> None:
 def nvls_sgd(p, buf, mc_g, mc_out, n, link, *, lr, mu, dampening, wd, grad_scale, first_step,
              g_dtype, dyn=None) -> None:
     _check(lib().frl_nvls_sgd(_ptr(p), _ptr(buf), mc_g, mc_out, n, link.rank, link.world,
-                              link.pads_dev, link.pad_base, link.max_blocks, lr, mu, dampening, wd,
+                              link.pads_dev, link.pad_base, _ptr(link.scratch), link.max_blocks, lr, mu, dampening, wd,
                               grad_scale, _ptr(dyn), int(first_step), g_dtype, _stream()),
            "frl_nvls_sgd")
 
@@ -239,7 +239,7 @@ def nvls_sgd(p, buf, mc_g, mc_out, n, link, *, lr, mu, dampening, wd, grad_scale
 def nvls_adam(p, m, v, vmax, mc_g, mc_out, n, link, *, lr, beta1, beta2, eps, wd, step, grad_scale,
               g_dtype, dyn=None) -> None:
     _check(lib().frl_nvls_adam(_ptr(p), _ptr(m), _ptr(v), _ptr(vmax), mc_g, mc_out, n, link.rank,
-                               link.world, link.pads_dev, link.pad_base, link.max_blocks, lr, beta1,
+                               link.world, link.pads_dev, link.pad_base, _ptr(link.scratch), link.max_blocks, lr, beta1,
                                beta2, eps, wd, step, grad_scale, _ptr(dyn), g_dtype, _stream()),
            "frl_nvls_adam")
 
@@ -247,6 +247,6 @@ def nvls_adam(p, m, v, vmax, mc_g, mc_out, n, link, *, lr, beta1, beta2, eps, wd
 def nvls_rmsprop(p, sq, buf, mc_g, mc_out, n, link, *, lr, alpha, eps, wd, mu, grad_scale, g_dtype,
                  dyn=None) -> None:
     _check(lib().frl_nvls_rmsprop(_ptr(p), _ptr(sq), _ptr(buf), mc_g, mc_out, n, link.rank,
-                                  link.world, link.pads_dev, link.pad_base, link.max_blocks, lr,
+                                  link.world, link.pads_dev, link.pad_base, _ptr(link.scratch), link.max_blocks, lr,
                                   alpha, eps, wd, mu, grad_scale, _ptr(dyn), g_dtype, _stream()),
            "frl_nvls_rmsprop")

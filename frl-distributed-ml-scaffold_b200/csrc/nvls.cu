@@ -18,9 +18,10 @@
 // bytes) — what an NVLS all-reduce alone moves — and divides the optimizer's HBM traffic and
 // state updates by world_size.  No NCCL call, no separate update launch.
 //
-// Cross-GPU synchronisation uses the symmetric-memory signal pads: block b of rank r raises flag
-// (b, r) in every peer's pad and waits for flag (b, peer) in its own (CAS 0->1 / 1->0), so all
-// ranks must launch the same grid.  Data movement is 16 bytes per multimem instruction.
+// Cross-GPU synchronisation uses the symmetric-memory signal pads: block 0 of rank r raises flag r
+// in every peer's pad and consumes flag `peer` in its own (CAS 0->1 / 1->0, system scope), then
+// releases / collects the other blocks through local flags, so the grid can span every SM.
+// Data movement is 16 bytes per multimem instruction.
 #include "frl_common.cuh"
 #include "optim_rules.cuh"
 
@@ -42,13 +43,13 @@ __device__ __forceinline__ void mm_st_b128(void* mc, uint32_t a, uint32_t b, uin
                  :: "l"(mc), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// All ranks' block `blockIdx.x` meet.  Threads 0..world-1 each handle one peer.
-__device__ __forceinline__ void meet_peers(uint32_t* const* pads, int rank, int world, int base) {
-    __syncthreads();
+// Cross-GPU rendezvous, done by block 0 only: thread t < world raises flag `rank` in peer t's pad
+// and consumes flag `t` in its own (CAS 0->1 / 1->0, system scope).
+__device__ __forceinline__ void meet_peers_block0(uint32_t* const* pads, int rank, int world, int base) {
     if (threadIdx.x < world) {
         const int peer = threadIdx.x;
-        uint32_t* put = pads[peer] + base + blockIdx.x * world + rank;
-        uint32_t* wait = pads[rank] + base + blockIdx.x * world + peer;
+        uint32_t* put = pads[peer] + base + rank;
+        uint32_t* wait = pads[rank] + base + peer;
         __threadfence_system();                                   // release everything before
         while (atomicCAS_system(put, 0u, 1u) != 0u) {}
         while (atomicCAS_system(wait, 1u, 0u) != 1u) {}
@@ -57,8 +58,44 @@ __device__ __forceinline__ void meet_peers(uint32_t* const* pads, int rank, int 
     __syncthreads();
 }
 
+// local scratch (uint32, zero-initialised once): [0] = finished-block counter, [8 + b] = go flag of block b
+__device__ __forceinline__ void kernel_entry_barrier(uint32_t* const* pads, int rank, int world, int base,
+                                                     uint32_t* local) {
+    if (blockIdx.x == 0) {
+        meet_peers_block0(pads, rank, world, base);               // every rank's gradients are written
+        for (int b = threadIdx.x + 1; b < static_cast<int>(gridDim.x); b += blockDim.x)
+            atomicExch(local + 8 + b, 1u);                        // release the other blocks
+    } else {
+        if (threadIdx.x == 0) {
+            while (atomicCAS(local + 8 + blockIdx.x, 1u, 0u) != 1u) {}
+            __threadfence();
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void kernel_exit_barrier(uint32_t* const* pads, int rank, int world, int base,
+                                                    uint32_t* local) {
+    __syncthreads();
+    if (blockIdx.x != 0) {
+        if (threadIdx.x == 0) {
+            __threadfence_system();                               // my multimem stores before the count
+            atomicAdd(local, 1u);
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        while (atomicAdd(local, 0u) != gridDim.x - 1) {}
+        atomicExch(local, 0u);
+        __threadfence_system();
+    }
+    __syncthreads();
+    meet_peers_block0(pads, rank, world, base + 32);              // every replica has every shard
+}
+
 struct NvlsCommon {
     uint32_t* const* pads;
+    uint32_t* local;
     int rank, world, pad_base;
     int64_t n;            // bucket elements
     float gscale;
@@ -72,7 +109,7 @@ nvls_update_bf16(float* __restrict__ p_, float* __restrict__ s0_, float* __restr
                  float* __restrict__ s2_, const __nv_bfloat16* mc_g, __nv_bfloat16* mc_lp,
                  Rule rule, NvlsCommon c) {
     if (c.dyn) rule.patch(c.dyn);
-    meet_peers(c.pads, c.rank, c.world, c.pad_base);
+    kernel_entry_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
     const int64_t per = ((c.n + c.world - 1) / c.world + 7) / 8 * 8;
     const int64_t lo = static_cast<int64_t>(c.rank) * per;
     int64_t hi = lo + per;
@@ -125,7 +162,7 @@ nvls_update_bf16(float* __restrict__ p_, float* __restrict__ s0_, float* __restr
                        pack_bf16(vp[u][1].x, vp[u][1].y), pack_bf16(vp[u][1].z, vp[u][1].w));
         }
     }
-    meet_peers(c.pads, c.rank, c.world, c.pad_base);
+    kernel_exit_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
 }
 
 // FP32 mode: fp32 gradients in, parameters ARE the master: multicast the new fp32 weights.
@@ -134,7 +171,7 @@ __global__ void __launch_bounds__(kNThreads)
 nvls_update_f32(const float* __restrict__ p_, float* __restrict__ s0_, float* __restrict__ s1_,
                 float* __restrict__ s2_, const float* mc_g, float* mc_p, Rule rule, NvlsCommon c) {
     if (c.dyn) rule.patch(c.dyn);
-    meet_peers(c.pads, c.rank, c.world, c.pad_base);
+    kernel_entry_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
     const int64_t per = ((c.n + c.world - 1) / c.world + 7) / 8 * 8;
     const int64_t lo = static_cast<int64_t>(c.rank) * per;
     int64_t hi = lo + per;
@@ -161,22 +198,24 @@ nvls_update_f32(const float* __restrict__ p_, float* __restrict__ s0_, float* __
         mm_st_b128(mc_p + e, __float_as_uint(vp.x), __float_as_uint(vp.y), __float_as_uint(vp.z),
                    __float_as_uint(vp.w));
     }
-    meet_peers(c.pads, c.rank, c.world, c.pad_base);
+    kernel_exit_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
 }
 
 template <typename Rule, int NS>
 static int launch_nvls(const Rule& rule, float* p, float* s0, float* s1, float* s2, const void* mc_g,
                        void* mc_out, int64_t n, int rank, int world, void* const* pads, int pad_base,
-                       int max_blocks, double gscale, const float* dyn, int g_dtype, void* stream,
-                       const char* name) {
+                       void* local_scratch, int max_blocks, double gscale, const float* dyn, int g_dtype,
+                       void* stream, const char* name) {
     FRL_REQUIRE(p && mc_g && mc_out && pads, FRL_E_ARG, "%s: null pointer", name);
     FRL_REQUIRE(world >= 2 && world <= 32 && rank >= 0 && rank < world, FRL_E_ARG, "%s: rank/world", name);
     FRL_REQUIRE(n >= 0 && n % 8 == 0, FRL_E_ARG, "%s: bucket size must be a multiple of 8 elements", name);
     FRL_REQUIRE(g_dtype == FRL_F32 || g_dtype == FRL_BF16, FRL_E_DTYPE, "%s: g_dtype", name);
     FRL_REQUIRE(aligned16(p) && aligned16(s0) && aligned16(s1) && aligned16(s2) && aligned16(mc_g) &&
                 aligned16(mc_out), FRL_E_ALIGN, "%s: 16-byte alignment", name);
-    FRL_REQUIRE(max_blocks >= 1 && max_blocks <= 64, FRL_E_ARG, "%s: max_blocks in 1..64", name);
-    NvlsCommon c{reinterpret_cast<uint32_t* const*>(pads), rank, world, pad_base, n,
+    FRL_REQUIRE(max_blocks >= 1 && max_blocks <= 1024 && local_scratch, FRL_E_ARG,
+                "%s: max_blocks in 1..1024 and a local scratch are required", name);
+    NvlsCommon c{reinterpret_cast<uint32_t* const*>(pads), static_cast<uint32_t*>(local_scratch), rank,
+                 world, pad_base, n,
                  static_cast<float>(gscale), dyn};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // the grid must be identical on every rank: it depends on arguments only
@@ -194,45 +233,45 @@ static int launch_nvls(const Rule& rule, float* p, float* s0, float* s1, float* 
 using namespace frl;
 
 extern "C" int frl_nvls_sgd(float* p, float* buf, const void* mc_g, void* mc_out, int64_t n, int rank,
-                            int world, void* const* signal_pads_dev, int pad_base, int max_blocks,
-                            double lr, double mu, double dampening, double wd, double grad_scale,
+                            int world, void* const* signal_pads_dev, int pad_base, void* local_scratch,
+                            int max_blocks, double lr, double mu, double dampening, double wd, double grad_scale,
                             const float* dyn, int first_step, int g_dtype, void* stream) {
     FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_nvls_sgd: momentum needs buf");
     const SgdRule r = make_sgd_rule(lr, mu, dampening, wd, first_step);
     if (mu != 0.0)
         return launch_nvls<SgdRule, 1>(r, p, buf, nullptr, nullptr, mc_g, mc_out, n, rank, world,
-                                       signal_pads_dev, pad_base, max_blocks, grad_scale, dyn, g_dtype,
+                                       signal_pads_dev, pad_base, local_scratch, max_blocks, grad_scale, dyn, g_dtype,
                                        stream, "frl_nvls_sgd");
     return launch_nvls<SgdRule, 0>(r, p, nullptr, nullptr, nullptr, mc_g, mc_out, n, rank, world,
-                                   signal_pads_dev, pad_base, max_blocks, grad_scale, dyn, g_dtype, stream,
+                                   signal_pads_dev, pad_base, local_scratch, max_blocks, grad_scale, dyn, g_dtype, stream,
                                    "frl_nvls_sgd");
 }
 
 extern "C" int frl_nvls_adam(float* p, float* m, float* v, float* vmax, const void* mc_g, void* mc_out,
                              int64_t n, int rank, int world, void* const* signal_pads_dev, int pad_base,
-                             int max_blocks, double lr, double beta1, double beta2, double eps, double wd,
+                             void* local_scratch, int max_blocks, double lr, double beta1, double beta2, double eps, double wd,
                              int64_t step, double grad_scale, const float* dyn, int g_dtype, void* stream) {
     FRL_REQUIRE(m && v && step >= 1, FRL_E_ARG, "frl_nvls_adam: state/step");
     if (vmax)
         return launch_nvls<AdamRule<true>, 3>(make_adam_rule<true>(lr, beta1, beta2, eps, wd, step), p, m, v,
                                               vmax, mc_g, mc_out, n, rank, world, signal_pads_dev, pad_base,
-                                              max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_adam");
+                                              local_scratch, max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_adam");
     return launch_nvls<AdamRule<false>, 2>(make_adam_rule<false>(lr, beta1, beta2, eps, wd, step), p, m, v,
                                            nullptr, mc_g, mc_out, n, rank, world, signal_pads_dev, pad_base,
-                                           max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_adam");
+                                           local_scratch, max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_adam");
 }
 
 extern "C" int frl_nvls_rmsprop(float* p, float* sq, float* buf, const void* mc_g, void* mc_out, int64_t n,
                                 int rank, int world, void* const* signal_pads_dev, int pad_base,
-                                int max_blocks, double lr, double alpha, double eps, double wd, double mu,
+                                void* local_scratch, int max_blocks, double lr, double alpha, double eps, double wd, double mu,
                                 double grad_scale, const float* dyn, int g_dtype, void* stream) {
     FRL_REQUIRE(sq, FRL_E_ARG, "frl_nvls_rmsprop: null sq");
     FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_nvls_rmsprop: momentum needs buf");
     if (mu != 0.0)
         return launch_nvls<RmspropRule<true>, 2>(make_rmsprop_rule<true>(lr, alpha, eps, wd, mu), p, sq, buf,
                                                  nullptr, mc_g, mc_out, n, rank, world, signal_pads_dev, pad_base,
-                                                 max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_rmsprop");
+                                                 local_scratch, max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_rmsprop");
     return launch_nvls<RmspropRule<false>, 1>(make_rmsprop_rule<false>(lr, alpha, eps, wd, mu), p, sq, nullptr,
                                               nullptr, mc_g, mc_out, n, rank, world, signal_pads_dev, pad_base,
-                                              max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_rmsprop");
+                                              local_scratch, max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_rmsprop");
 }

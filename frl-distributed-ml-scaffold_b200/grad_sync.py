@@ -88,7 +88,8 @@ class GradBucketPipeline:
         for s in arena.slots:
             self._handles.append(s.param.register_post_accumulate_grad_hook(self._make_hook(s)))
 
-        self.side_stream = torch.cuda.Stream(device=arena.device) if self.on_cuda else None
+        # high priority: the (short) reduce/update kernels should not queue behind GEMM CTAs
+        self.side_stream = torch.cuda.Stream(device=arena.device, priority=-1) if self.on_cuda else None
         self.clip_out = None
         self.clip_scratch = None
         if self.clip_norm > 0.0:

@@ -265,7 +265,7 @@ class Solver:
             from .symm import make_link
             nvls_link = make_link(symm_alloc, arena.grad,
                                   arena.lp if arena.lp is not None else arena.master,
-                                  max_blocks=int(os.environ.get("FRL_B200_NVLS_BLOCKS", "32")))
+                                  max_blocks=int(os.environ.get("FRL_B200_NVLS_BLOCKS", "148")))
         pipeline = GradBucketPipeline(
             arena, optimizer, world_size=args.world_size, clip_norm=run_opts.optim.gradientClip,
             nvls_link=nvls_link,

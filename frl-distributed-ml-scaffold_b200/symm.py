@@ -19,7 +19,7 @@ logger = logging.getLogger(__name__)
 class NvlsLink:
     """What the K7 launches need besides the bucket pointers."""
     __slots__ = ("rank", "world", "pads_dev", "pad_base", "max_blocks", "mc_grad", "mc_out",
-                 "grad_esz", "out_esz", "handles")
+                 "grad_esz", "out_esz", "handles", "scratch")
 
     def __init__(self):
         self.handles = []
@@ -77,8 +77,10 @@ def make_link(alloc: SymmetricAllocator, grad: torch.Tensor, out: torch.Tensor,
     link.rank, link.world = hg.rank, hg.world_size
     link.pads_dev = hg.signal_pad_ptrs_dev
     link.pad_base = 0
-    pad_words = hg.signal_pad_size // 4
-    link.max_blocks = max(1, min(max_blocks, 64, pad_words // max(link.world, 1)))
+    if hg.signal_pad_size // 4 < 64 or link.world > 32:
+        raise RuntimeError("signal pad too small")
+    link.max_blocks = max(1, min(max_blocks, 1024))
+    link.scratch = torch.zeros(8 + link.max_blocks, dtype=torch.int32, device=grad.device)
     link.mc_grad, link.mc_out = hg.multicast_ptr, ho.multicast_ptr
     link.grad_esz, link.out_esz = grad.element_size(), out.element_size()
     link.handles = [hg, ho]

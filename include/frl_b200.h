@@ -182,21 +182,24 @@ int frl_colsum(const void* x, int x_dtype, int64_t rows, int64_t cols, void* out
  *                      from: bf16 shadow weights (g_dtype FRL_BF16) or the fp32 master
  *                      (g_dtype FRL_F32, where p is that same memory, locally addressed)
  *   signal_pads_dev    device array [world] of pointers to each rank's uint32 signal pad;
- *                      slots [pad_base, pad_base + max_blocks*world) are used
- *   max_blocks         grid size; MUST be the same on every rank (1..64)
+ *                      slots [pad_base, pad_base + 64) are used
+ *   local_scratch      rank-local uint32[8 + max_blocks], zero-initialised once
+ *   max_blocks         grid size (1..1024, all blocks must be co-resident)
  * n must be a multiple of 8; launch order must be identical on all ranks.
  * ---------------------------------------------------------------------------------------- */
 int frl_nvls_sgd(float* p, float* buf, const void* mc_g, void* mc_out, int64_t n, int rank,
-                 int world, void* const* signal_pads_dev, int pad_base, int max_blocks,
-                 double lr, double mu, double dampening, double wd, double grad_scale,
+                 int world, void* const* signal_pads_dev, int pad_base, void* local_scratch,
+                 int max_blocks, double lr, double mu, double dampening, double wd, double grad_scale,
                  const float* dyn, int first_step, int g_dtype, void* stream);
 int frl_nvls_adam(float* p, float* m, float* v, float* vmax, const void* mc_g, void* mc_out,
                   int64_t n, int rank, int world, void* const* signal_pads_dev, int pad_base,
-                  int max_blocks, double lr, double beta1, double beta2, double eps, double wd,
+                  void* local_scratch, int max_blocks, double lr, double beta1, double beta2,
+                  double eps, double wd,
                   int64_t step, double grad_scale, const float* dyn, int g_dtype, void* stream);
 int frl_nvls_rmsprop(float* p, float* sq, float* buf, const void* mc_g, void* mc_out, int64_t n,
                      int rank, int world, void* const* signal_pads_dev, int pad_base,
-                     int max_blocks, double lr, double alpha, double eps, double wd, double mu,
+                     void* local_scratch, int max_blocks, double lr, double alpha, double eps,
+                     double wd, double mu,
                      double grad_scale, const float* dyn, int g_dtype, void* stream);
 
 #ifdef __cplusplus
