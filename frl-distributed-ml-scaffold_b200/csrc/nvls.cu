@@ -28,7 +28,6 @@
 namespace frl {
 
 constexpr int kNThreads = 512;
-constexpr int kNUnroll = 2;
 
 __device__ __forceinline__ void mm_ld_reduce_bf16x8(const void* mc, uint32_t (&r)[4]) {
     asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
@@ -103,6 +102,11 @@ struct NvlsCommon {
 };
 
 // BF16 mode: bf16 gradients in, fp32 master/state local, bf16 shadow multicast out. 8 elems / item.
+// The switch round trip of multimem.ld_reduce is the long latency here (microseconds), so every
+// thread first issues kNRemote of them back to back and only then walks the items, loading the
+// (short-latency) local master/state slices item by item.
+constexpr int kNRemote = 4;
+
 template <typename Rule, int NS>
 __global__ void __launch_bounds__(kNThreads)
 nvls_update_bf16(float* __restrict__ p_, float* __restrict__ s0_, float* __restrict__ s1_,
@@ -116,50 +120,46 @@ nvls_update_bf16(float* __restrict__ p_, float* __restrict__ s0_, float* __restr
     if (hi > c.n) hi = c.n;
     const int64_t items = hi > lo ? (hi - lo + 7) / 8 : 0;        // arena buckets are multiples of 8
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kNThreads;
+    const f32x4 zero{0.f, 0.f, 0.f, 0.f};
+    const float gs = c.gscale;
     for (int64_t it0 = static_cast<int64_t>(blockIdx.x) * kNThreads + threadIdx.x; it0 < items;
-         it0 += stride * kNUnroll) {
-        uint32_t g[kNUnroll][4];
-        f32x4 vp[kNUnroll][2], a0[kNUnroll][2], a1[kNUnroll][2], a2[kNUnroll][2];
-        const f32x4 zero{0.f, 0.f, 0.f, 0.f};
+         it0 += stride * kNRemote) {
+        uint32_t g[kNRemote][4];
 #pragma unroll
-        for (int u = 0; u < kNUnroll; ++u) {
+        for (int u = 0; u < kNRemote; ++u) {
             const int64_t it = it0 + u * stride;
-            if (it >= items) break;
-            const int64_t e = lo + it * 8;
-            mm_ld_reduce_bf16x8(mc_g + e, g[u]);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                vp[u][h] = ld_stream(reinterpret_cast<const f32x4*>(p_ + e) + h);
-                a0[u][h] = NS > 0 ? ld_stream(reinterpret_cast<const f32x4*>(s0_ + e) + h) : zero;
-                a1[u][h] = NS > 1 ? ld_stream(reinterpret_cast<const f32x4*>(s1_ + e) + h) : zero;
-                a2[u][h] = NS > 2 ? ld_stream(reinterpret_cast<const f32x4*>(s2_ + e) + h) : zero;
-            }
+            if (it < items) mm_ld_reduce_bf16x8(mc_g + lo + it * 8, g[u]);
         }
 #pragma unroll
-        for (int u = 0; u < kNUnroll; ++u) {
+        for (int u = 0; u < kNRemote; ++u) {
             const int64_t it = it0 + u * stride;
             if (it >= items) break;
             const int64_t e = lo + it * 8;
-            const float gs = c.gscale;
-            f32x4 g0{bf16lo(g[u][0]) * gs, bf16hi(g[u][0]) * gs, bf16lo(g[u][1]) * gs, bf16hi(g[u][1]) * gs};
-            f32x4 g1{bf16lo(g[u][2]) * gs, bf16hi(g[u][2]) * gs, bf16lo(g[u][3]) * gs, bf16hi(g[u][3]) * gs};
-            rule(vp[u][0].x, g0.x, a0[u][0].x, a1[u][0].x, a2[u][0].x);
-            rule(vp[u][0].y, g0.y, a0[u][0].y, a1[u][0].y, a2[u][0].y);
-            rule(vp[u][0].z, g0.z, a0[u][0].z, a1[u][0].z, a2[u][0].z);
-            rule(vp[u][0].w, g0.w, a0[u][0].w, a1[u][0].w, a2[u][0].w);
-            rule(vp[u][1].x, g1.x, a0[u][1].x, a1[u][1].x, a2[u][1].x);
-            rule(vp[u][1].y, g1.y, a0[u][1].y, a1[u][1].y, a2[u][1].y);
-            rule(vp[u][1].z, g1.z, a0[u][1].z, a1[u][1].z, a2[u][1].z);
-            rule(vp[u][1].w, g1.w, a0[u][1].w, a1[u][1].w, a2[u][1].w);
+            f32x4 vp[2], a0[2], a1[2], a2[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                st_stream(reinterpret_cast<f32x4*>(p_ + e) + h, vp[u][h]);
-                if (NS > 0) st_stream(reinterpret_cast<f32x4*>(s0_ + e) + h, a0[u][h]);
-                if (NS > 1) st_stream(reinterpret_cast<f32x4*>(s1_ + e) + h, a1[u][h]);
-                if (NS > 2) st_stream(reinterpret_cast<f32x4*>(s2_ + e) + h, a2[u][h]);
+                vp[h] = ld_stream(reinterpret_cast<const f32x4*>(p_ + e) + h);
+                a0[h] = NS > 0 ? ld_stream(reinterpret_cast<const f32x4*>(s0_ + e) + h) : zero;
+                a1[h] = NS > 1 ? ld_stream(reinterpret_cast<const f32x4*>(s1_ + e) + h) : zero;
+                a2[h] = NS > 2 ? ld_stream(reinterpret_cast<const f32x4*>(s2_ + e) + h) : zero;
             }
-            mm_st_b128(mc_lp + e, pack_bf16(vp[u][0].x, vp[u][0].y), pack_bf16(vp[u][0].z, vp[u][0].w),
-                       pack_bf16(vp[u][1].x, vp[u][1].y), pack_bf16(vp[u][1].z, vp[u][1].w));
+            rule(vp[0].x, bf16lo(g[u][0]) * gs, a0[0].x, a1[0].x, a2[0].x);
+            rule(vp[0].y, bf16hi(g[u][0]) * gs, a0[0].y, a1[0].y, a2[0].y);
+            rule(vp[0].z, bf16lo(g[u][1]) * gs, a0[0].z, a1[0].z, a2[0].z);
+            rule(vp[0].w, bf16hi(g[u][1]) * gs, a0[0].w, a1[0].w, a2[0].w);
+            rule(vp[1].x, bf16lo(g[u][2]) * gs, a0[1].x, a1[1].x, a2[1].x);
+            rule(vp[1].y, bf16hi(g[u][2]) * gs, a0[1].y, a1[1].y, a2[1].y);
+            rule(vp[1].z, bf16lo(g[u][3]) * gs, a0[1].z, a1[1].z, a2[1].z);
+            rule(vp[1].w, bf16hi(g[u][3]) * gs, a0[1].w, a1[1].w, a2[1].w);
+            mm_st_b128(mc_lp + e, pack_bf16(vp[0].x, vp[0].y), pack_bf16(vp[0].z, vp[0].w),
+                       pack_bf16(vp[1].x, vp[1].y), pack_bf16(vp[1].z, vp[1].w));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                st_stream(reinterpret_cast<f32x4*>(p_ + e) + h, vp[h]);
+                if (NS > 0) st_stream(reinterpret_cast<f32x4*>(s0_ + e) + h, a0[h]);
+                if (NS > 1) st_stream(reinterpret_cast<f32x4*>(s1_ + e) + h, a1[h]);
+                if (NS > 2) st_stream(reinterpret_cast<f32x4*>(s2_ + e) + h, a2[h]);
+            }
         }
     }
     kernel_exit_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
@@ -178,25 +178,35 @@ nvls_update_f32(const float* __restrict__ p_, float* __restrict__ s0_, float* __
     if (hi > c.n) hi = c.n;
     const int64_t items = hi > lo ? (hi - lo + 3) / 4 : 0;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kNThreads;
-    for (int64_t it = static_cast<int64_t>(blockIdx.x) * kNThreads + threadIdx.x; it < items; it += stride) {
-        const int64_t e = lo + it * 4;
-        float g[4];
-        mm_ld_reduce_f32x4(mc_g + e, g);
-        f32x4 vp = ld_stream(reinterpret_cast<const f32x4*>(p_ + e));
-        const f32x4 zero{0.f, 0.f, 0.f, 0.f};
-        f32x4 a0 = NS > 0 ? ld_stream(reinterpret_cast<const f32x4*>(s0_ + e)) : zero;
-        f32x4 a1 = NS > 1 ? ld_stream(reinterpret_cast<const f32x4*>(s1_ + e)) : zero;
-        f32x4 a2 = NS > 2 ? ld_stream(reinterpret_cast<const f32x4*>(s2_ + e)) : zero;
-        const float gs = c.gscale;
-        rule(vp.x, g[0] * gs, a0.x, a1.x, a2.x);
-        rule(vp.y, g[1] * gs, a0.y, a1.y, a2.y);
-        rule(vp.z, g[2] * gs, a0.z, a1.z, a2.z);
-        rule(vp.w, g[3] * gs, a0.w, a1.w, a2.w);
-        if (NS > 0) st_stream(reinterpret_cast<f32x4*>(s0_ + e), a0);
-        if (NS > 1) st_stream(reinterpret_cast<f32x4*>(s1_ + e), a1);
-        if (NS > 2) st_stream(reinterpret_cast<f32x4*>(s2_ + e), a2);
-        mm_st_b128(mc_p + e, __float_as_uint(vp.x), __float_as_uint(vp.y), __float_as_uint(vp.z),
-                   __float_as_uint(vp.w));
+    const f32x4 zero{0.f, 0.f, 0.f, 0.f};
+    const float gs = c.gscale;
+    for (int64_t it0 = static_cast<int64_t>(blockIdx.x) * kNThreads + threadIdx.x; it0 < items;
+         it0 += stride * kNRemote) {
+        float g[kNRemote][4];
+#pragma unroll
+        for (int u = 0; u < kNRemote; ++u) {
+            const int64_t it = it0 + u * stride;
+            if (it < items) mm_ld_reduce_f32x4(mc_g + lo + it * 4, g[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kNRemote; ++u) {
+            const int64_t it = it0 + u * stride;
+            if (it >= items) break;
+            const int64_t e = lo + it * 4;
+            f32x4 vp = ld_stream(reinterpret_cast<const f32x4*>(p_ + e));
+            f32x4 a0 = NS > 0 ? ld_stream(reinterpret_cast<const f32x4*>(s0_ + e)) : zero;
+            f32x4 a1 = NS > 1 ? ld_stream(reinterpret_cast<const f32x4*>(s1_ + e)) : zero;
+            f32x4 a2 = NS > 2 ? ld_stream(reinterpret_cast<const f32x4*>(s2_ + e)) : zero;
+            rule(vp.x, g[u][0] * gs, a0.x, a1.x, a2.x);
+            rule(vp.y, g[u][1] * gs, a0.y, a1.y, a2.y);
+            rule(vp.z, g[u][2] * gs, a0.z, a1.z, a2.z);
+            rule(vp.w, g[u][3] * gs, a0.w, a1.w, a2.w);
+            mm_st_b128(mc_p + e, __float_as_uint(vp.x), __float_as_uint(vp.y), __float_as_uint(vp.z),
+                       __float_as_uint(vp.w));
+            if (NS > 0) st_stream(reinterpret_cast<f32x4*>(s0_ + e), a0);
+            if (NS > 1) st_stream(reinterpret_cast<f32x4*>(s1_ + e), a1);
+            if (NS > 2) st_stream(reinterpret_cast<f32x4*>(s2_ + e), a2);
+        }
     }
     kernel_exit_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
 }

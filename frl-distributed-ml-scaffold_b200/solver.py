@@ -186,6 +186,21 @@ def _fork_is_safe() -> bool:
     return os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> bool:
+    """Pin this rank's threads to the CPUs nearest its GPU (NVML's ideal affinity), so pinned
+    staging buffers are first-touched on the local NUMA node and H2D copies do not cross sockets.
+    Best effort: returns False if NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception as e:                           # noqa: BLE001
+        logger.info("NUMA binding skipped: %s", e)
+        return False
+
+
 def resolve_precision(explicit: Optional[Precision] = None) -> Precision:
     if explicit is not None:
         return explicit
@@ -222,6 +237,8 @@ class Solver:
             raise RuntimeError("frl_b200 has no CPU path: a CUDA (sm_100a) device is required")
         torch.cuda.set_device(args.local_rank)
         device = torch.device("cuda", args.local_rank)
+        if args.world_size > 1 and os.environ.get("FRL_B200_NUMA_BIND", "1") != "0":
+            bind_to_gpu_numa_node(args.local_rank)
         logger.info("Using device %s" % device)
 
         checkpoint: Optional[Checkpoint] = None
