@@ -27,6 +27,10 @@ from .types import Precision
 
 logger = logging.getLogger(__name__)
 
+#: kernels of this library executed through graph replays (the C-side launch counter only sees
+#: direct launches): each replay adds the number of frl_* launches recorded at capture time
+REPLAYED_LAUNCHES = 0
+
 
 def _signature(data: Sequence[torch.Tensor], target) -> Tuple:
     sig = [(tuple(t.shape), t.dtype) for t in data]
@@ -93,6 +97,7 @@ class _Captured:
         gc.collect()                  # free autograd graphs of earlier (eager) steps
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        launches_before = _native.launch_count()
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             if w.buffers is not None:
                 w.buffers.sync()
@@ -105,6 +110,7 @@ class _Captured:
         # replay performs the step for real (finish_step(defer_tail=True) left the optimizer's
         # step counter to run_tail())
         w.pipeline.step_id -= 1
+        self.frl_kernels = _native.launch_count() - launches_before
         self.output = [o.detach() for o in output]
         self.names = list(sub.keys())
         self._total, self._sub = total.detach(), {k: v.detach() for k, v in sub.items()}
@@ -129,6 +135,8 @@ class _Captured:
         self._fill(data, target)
         w.optimizer.refresh_dynamic_scalars()
         self.graph.replay()
+        global REPLAYED_LAUNCHES
+        REPLAYED_LAUNCHES += self.frl_kernels
         w.pipeline.step_id += 1
         w.pipeline.run_tail()                 # tail update (1 GPU / clipping) + step counter
         if sink_row is not None:
