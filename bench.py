@@ -347,67 +347,60 @@ def main_b200(args, rank, local_rank, world):
     # ======================= leg 2: end to end from host buffers =======================
     e2e = None
     if not args.no_e2e:
-        host = []
-        for data, target in pool:
-            host.append(([d.cpu().pin_memory() for d in data],
-                         [tuple(tt.cpu().pin_memory() for tt in head) for head in target]))
-        h2d_bytes = sum(d.numel() * d.element_size() for d in host[0][0]) + sum(
-            tt.numel() * tt.element_size() for head in host[0][1] for tt in head)
-        copy_stream = torch.cuda.Stream(device=dev)
-        slots = [([torch.empty_like(d, device=dev) for d in host[0][0]],
-                  [tuple(torch.empty_like(tt, device=dev) for tt in head) for head in host[0][1]])
-                 for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        freed = [torch.cuda.Event() for _ in range(2)]
-        for ev in freed:
-            ev.record()
+        # The dataset (fp32, 16 batches per rank) lives in pinned host memory behind the Problem's
+        # `datasets`; the loop's own DeviceBatchLoader shuffles it, pulls the rows of the next
+        # batch over PCIe (frl_gather_rows on a copy stream) while the current one trains, and runs
+        # the transform on the device (frl_preproc_affine -> bf16).  The criterion kernel's loss
+        # row goes to the pinned loss log and is read by the host 2 steps late.
+        from frl_b200.device_loader import DeviceBatchLoader
+        from frl_b200 import synthetic as syn
+        n_host = 16 * B
+        host_problem = syn.make_mlp_problem(ns, save_dir, n_train=n_host, width=WIDTH,
+                                            n_classes=N_CLASSES, reg_dim=REG_DIM, depth=DEPTH, pinned=True)
+        host_ds = host_problem.datasets[0]
+        out_dtype = torch.bfloat16 if precision == Precision.BF16 else torch.float32
+        loader = DeviceBatchLoader(host_ds, batch_size=B, sampler=None, device=dev, out_dtype=out_dtype)
+        h2d_bytes = loader.h2d_bytes_per_batch
+        stream_iter = [iter(loader)]
 
-        def upload(i):
-            s = i % 2
-            src = host[i % POOL]
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[s])
-                for d, h in zip(slots[s][0], src[0]):
-                    d.copy_(h, non_blocking=True)
-                for dh, hh in zip(slots[s][1], src[1]):
-                    for d, h in zip(dh, hh):
-                        d.copy_(h, non_blocking=True)
-                ready[s].record()
+        def next_batch():
+            try:
+                return next(stream_iter[0])
+            except StopIteration:
+                stream_iter[0] = iter(loader)          # next epoch: reshuffle
+                return next(stream_iter[0])
 
         seen = []
 
-        def step_e2e(i, base):
-            s = i % 2
-            if i == 0:
-                upload(0)
-            upload(i + 1)                       # prefetch the next batch while this one computes
-            torch.cuda.current_stream().wait_event(ready[s])
-            worker.criterion.set_step_sink(log_ring.row(base + i), log_ring.nan_flag)
-            worker._pass_one_minibatch(base + i, t.Split.TRAIN, slots[s][0], slots[s][1])
-            freed[s].record()
-            log_ring.mark(base + i)
+        def step_e2e(i):
+            data, target, _meta = next_batch()
+            worker.criterion.set_step_sink(log_ring.row(i), log_ring.nan_flag)
+            worker._pass_one_minibatch(i, t.Split.TRAIN, data, target)
+            log_ring.mark(i)
             if i >= 2:                          # device -> host: the loss row the kernel wrote
-                log_ring.wait(base + i - 2)
-                seen.append(float(log_ring.rows[(base + i - 2) % log_ring.capacity, 0]))
+                log_ring.wait(i - 2)
+                seen.append(float(log_ring.rows[(i - 2) % log_ring.capacity, 0]))
 
-        # reuse the ring: e2e steps overwrite rows from 0
         for i in range(W):
-            step_e2e(i, 0)
+            step_e2e(i)
         barrier()
         seen.clear()
         m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         m0.record()
         for i in range(K):
-            step_e2e(W + i, 0)
+            step_e2e(W + i)
         m1.record()
         barrier()
         e2e_ms = max_over_ranks(m0.elapsed_time(m1))
+        assert all(x == x for x in seen), "NaN loss in the e2e leg"
         e2e = {"value": world * B * K / (e2e_ms / 1e3), "unit": "samples/s",
                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 * (1 + n_tasks),
                "ms_per_step": e2e_ms / K,
-               "how": "pinned host batch -> cudaMemcpyAsync on a copy stream (double-buffered, "
-                      "overlapped with the previous step) -> cast kernel -> step; loss row written "
-                      "to pinned host memory by the criterion kernel and read by the host 2 steps late",
+               "how": "Problem dataset (fp32) in pinned host memory -> DeviceBatchLoader: sampler "
+                      "indices, rows of the next batch pulled over PCIe by frl_gather_rows on a copy "
+                      "stream (overlapped with the current step), transform + bf16 cast on device -> "
+                      "SolverWorker._pass_one_minibatch; loss row written to pinned host memory by "
+                      "the criterion kernel, read by the host 2 steps late",
                "losses_read": len(seen)}
 
     # ======================= CPU baseline (rank 0, N=1) =======================

@@ -58,6 +58,7 @@ SIGNATURES = {
     "frl_cast_scale": (_i, [_vp, _i, _vp, _i, _i64, _f, _vp]),
     "frl_colsum_scratch_bytes": (_i64, [_i64, _i64]),
     "frl_colsum": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i, _vp, _vp]),
+    "frl_gather_rows": (_i, [_vp, _i64, _vp, _vp, _i64, _i64, _i, _vp]),
     "frl_nvls_sgd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d, _vp, _i, _i, _vp]),
     "frl_nvls_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d,
                            _i64, _d, _vp, _i, _vp]),
@@ -250,3 +251,15 @@ def nvls_rmsprop(p, sq, buf, mc_g, mc_out, n, link, *, lr, alpha, eps, wd, mu, g
                                   link.world, link.pads_dev, link.pad_base, _ptr(link.scratch), link.max_blocks, lr,
                                   alpha, eps, wd, mu, grad_scale, _ptr(dyn), g_dtype, _stream()),
            "frl_nvls_rmsprop")
+
+
+# ---- K8 -------------------------------------------------------------------------------------
+
+def gather_rows(src_pinned, idx_dev, dst, max_blocks: int = 64) -> None:
+    """dst[i] = src_pinned[idx[i]] — ``src_pinned`` is a pinned HOST tensor [rows, ...], ``dst`` a
+    device tensor [len(idx), ...]; the kernel reads host memory over PCIe."""
+    assert src_pinned.is_pinned() and src_pinned.is_contiguous() and dst.is_contiguous()
+    row_bytes = src_pinned[0].numel() * src_pinned.element_size() if src_pinned.shape[0] else 0
+    _check(lib().frl_gather_rows(_ptr(src_pinned), src_pinned.shape[0], _ptr(idx_dev), _ptr(dst),
+                                 idx_dev.numel(), row_bytes, max_blocks, _stream()),
+           "frl_gather_rows")

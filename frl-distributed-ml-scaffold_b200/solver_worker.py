@@ -359,9 +359,9 @@ class SolverWorker:
             with StepWatchdog(self.run_opts.minibatchTimeoutMs) as dog:
                 for minibatch_idx, (data, target, raw_meta) in enumerate(loader):
                     dog.kick()
-                    data = [t.to(self.device, non_blocking=True) for t in data]
-                    target = [tuple(t.to(self.device, non_blocking=True) for t in head)
-                              for head in target]
+                    data = [t if t.is_cuda else t.to(self.device, non_blocking=True) for t in data]
+                    target = [tuple(t if t.is_cuda else t.to(self.device, non_blocking=True)
+                                    for t in head) for head in target]
                     self.criterion.set_step_sink(log.row(minibatch_idx), log.nan_flag)
                     self.criterion._sink_written = False
                     output, total_loss, sub_loss, grad_norms = self._pass_one_minibatch(
@@ -632,6 +632,13 @@ class SolverWorker:
             if self.run_opts.maxEpochImages > 0:
                 logger.info("Using %d images per epoch." % self.run_opts.maxEpochImages)
                 dataset = SubsetMultifieldDataset(dataset, range(self.run_opts.maxEpochImages))
+            from .device_loader import DeviceBatchLoader, supports_device_batches
+            if self.device.type == "cuda" and supports_device_batches(dataset):
+                # raw dataset in pinned host memory: rows pulled by the GPU, transform on device
+                out_dtype = torch.bfloat16 if self.precision == Precision.BF16 else torch.float32
+                loaders[split] = DeviceBatchLoader(dataset, batch_size=batchSize, sampler=sampler,
+                                                   device=self.device, out_dtype=out_dtype)
+                continue
             loaders[split] = torch.utils.data.DataLoader(
                 dataset, batch_size=batchSize, shuffle=sampler is None,
                 num_workers=self.run_opts.numThreads,

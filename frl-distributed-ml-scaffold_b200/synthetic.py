@@ -76,6 +76,43 @@ def _array_dataset_class(ns):
     return ArrayDataset
 
 
+def _pinned_dataset_class(ns):
+    """ArrayDataset whose fields also exist as pinned host tensors + a batched device transform
+    (the B200 input path); the per-sample path stays available and equivalent."""
+    import torch
+    from . import _native
+    from .transform import DeviceBatchTransform
+    Base = _array_dataset_class(ns)
+
+    class AffineDeviceTransform(DeviceBatchTransform):
+        def __init__(self, shift: float, scale: float) -> None:
+            self.shift, self.scale = float(shift), float(scale)
+            self._coef = {}
+
+        def apply(self, raw, split, out_dtype):
+            x = raw["x"]
+            out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+            key = x.device
+            if key not in self._coef:          # y = x*scale + (-shift*scale)
+                self._coef[key] = (torch.tensor([self.scale], device=x.device),
+                                   torch.tensor([-self.shift * self.scale], device=x.device))
+            sc, bi = self._coef[key]
+            _native.preproc_affine(x, out, inner=max(x.numel(), 1), channels=1, scale=sc, bias=bi)
+            # task order is the Problem's: targets are looked up by the tasks' field names
+            return [out], [(raw[f],) for f in self.target_fields]
+
+    class PinnedArrayDataset(Base):
+        def __init__(self, split, fields, transform, shift, scale, target_fields) -> None:
+            super().__init__(split, fields, transform)
+            pin = torch.cuda.is_available()
+            self.pinned_fields = {k: (torch.from_numpy(v).pin_memory() if pin else torch.from_numpy(v))
+                                  for k, v in fields.items()}
+            self.device_transform = AffineDeviceTransform(shift, scale)
+            self.device_transform.target_fields = list(target_fields)
+
+    return PinnedArrayDataset
+
+
 def _task_classes(ns):
     class RegressionTask(ns.Task):
         def __init__(self, in_dim: int, out_dim: int, weight: float, field: str = "y_reg",
@@ -163,15 +200,22 @@ def _problem_class(ns):
         BatchMetaType = BatchMeta
 
         def __init__(self, tasks, trunk_dims: Sequence[int], datasets_fields, save_dir: str,
-                     shift: float, scale: float, criterion_kind: str = "parallel") -> None:
+                     shift: float, scale: float, criterion_kind: str = "parallel",
+                     pinned: bool = False) -> None:
             self._tasks = tasks
             self._trunk_dims = list(trunk_dims)
             self._save_dir = save_dir
             self._criterion_kind = criterion_kind
             self.transform = CenteringTransform(tasks, shift, scale)
-            ds_cls = _array_dataset_class(ns)
-            self._datasets = [ds_cls(split, fields, self.transform)
-                              for split, fields in datasets_fields]
+            if pinned:
+                ds_cls = _pinned_dataset_class(ns)
+                self._datasets = [ds_cls(split, fields, self.transform, shift, scale,
+                                         [t._field for t in tasks])
+                                  for split, fields in datasets_fields]
+            else:
+                ds_cls = _array_dataset_class(ns)
+                self._datasets = [ds_cls(split, fields, self.transform)
+                                  for split, fields in datasets_fields]
 
         @property
         def datasets(self):
@@ -219,18 +263,18 @@ def synthetic_fields(n: int, in_dim: int, reg_dim: int, n_classes: int, seed: in
 
 
 def make_toy_problem(ns, save_dir: str, n_train: int = 512, n_test: int = 128,
-                     criterion_kind: str = "parallel"):
+                     criterion_kind: str = "parallel", pinned: bool = False):
     """Config 1: trunk 64->128->128, reg head 128->4 (w 0.5), cls head 128->10 (w 2)."""
     Reg, Cls = _task_classes(ns)
     tasks = [Reg(128, 4, 0.5), Cls(128, 10, 2.0)]
     fields = [(ns.Split.TRAIN, synthetic_fields(n_train, 64, 4, 10, 0, True)),
               (ns.Split.TEST, synthetic_fields(n_test, 64, 4, 10, 1, True))]
     return _problem_class(ns)(tasks, [64, 128, 128], fields, save_dir, shift=0.5, scale=2.0,
-                              criterion_kind=criterion_kind)
+                              criterion_kind=criterion_kind, pinned=pinned)
 
 
 def make_mlp_problem(ns, save_dir: str, n_train: int = 8192, n_test: int = 0, width: int = 4096,
-                     n_classes: int = 1000, reg_dim: int = 64, depth: int = 3):
+                     n_classes: int = 1000, reg_dim: int = 64, depth: int = 3, pinned: bool = False):
     """Configs 2/3: trunk depth x [Linear(width,width)+ReLU], CE head width->1000 (w 1), MSE
     head width->64 (w 1); x ~ N(0,1)."""
     Reg, Cls = _task_classes(ns)
@@ -238,4 +282,5 @@ def make_mlp_problem(ns, save_dir: str, n_train: int = 8192, n_test: int = 0, wi
     fields = [(ns.Split.TRAIN, synthetic_fields(n_train, width, reg_dim, n_classes, 0, False))]
     if n_test:
         fields.append((ns.Split.TEST, synthetic_fields(n_test, width, reg_dim, n_classes, 1, False)))
-    return _problem_class(ns)(tasks, [width] * (depth + 1), fields, save_dir, shift=0.0, scale=1.0)
+    return _problem_class(ns)(tasks, [width] * (depth + 1), fields, save_dir, shift=0.0, scale=1.0,
+                              pinned=pinned)

@@ -38,12 +38,17 @@ class MultifieldTransform(ABC, Generic[SampleMetaT]):
 class DeviceBatchTransform(ABC):
     """Batched, on-device counterpart of ``MultifieldTransform`` (extension).
 
-    A dataset that can hand out whole raw batches (``get_raw_batch``) pairs with one of these:
-    ``stage`` lists the raw host tensors to ship (pinned, any dtype), ``apply`` turns the
-    device copies into ``(data, target)`` exactly as the per-sample transform would.
+    Pairs with a dataset whose raw fields sit in pinned host memory (``pinned_fields``): the
+    loop's ``DeviceBatchLoader`` pulls the rows of a batch into HBM and calls ``apply`` once per
+    batch with the device copies; ``apply`` must return ``(data, target)`` equal to what the
+    per-sample transform + ``default_collate`` would have produced (floating outputs in
+    ``out_dtype``).  ``meta`` returns the collated meta dict (tensors on any device / lists).
     """
 
     @abstractmethod
-    def apply(self, raw: Dict[str, Tensor], split: Split
+    def apply(self, raw: Dict[str, Tensor], split: Split, out_dtype
               ) -> Tuple[List[Tensor], List[Tuple[Tensor, ...]]]:
         ...
+
+    def meta(self, raw: Dict[str, Tensor], index: Tensor) -> Dict[str, Any]:
+        return {"index": index.clone()}

@@ -426,3 +426,23 @@ def test_linear_gradients_are_written_into_the_arena(precision):
     torch.testing.assert_close(results[1][0], results[0][0], **tol)      # same gradients
     torch.testing.assert_close(results[1][1], results[0][1], **tol)      # same weights after 3 steps
     assert "forward" not in fancy[0].__dict__                            # unpatched again
+
+
+# ------------------------------------------------------------------------------------------------
+# K8 + the batched device-side input path
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("rows,cols,dt", [(1000, 64, torch.float32), (257, 4096, torch.float32),
+                                          (64, 8, torch.int64), (33, 1024, torch.bfloat16)])
+def test_gather_rows_from_pinned_host_memory(rows, cols, dt):
+    src = (torch.randn(rows, cols) * 100).to(dt).pin_memory()
+    idx = torch.randint(0, rows, (123,), dtype=torch.int64)
+    dst = torch.zeros(123, cols, dtype=dt, device=DEV)
+    _native.gather_rows(src, idx.to(DEV), dst)
+    torch.cuda.synchronize()
+    assert torch.equal(dst.cpu(), src[idx])
+    # out-of-range indices never read outside the dataset (clamped to row 0)
+    bad = torch.tensor([rows + 5, -1], dtype=torch.int64, device=DEV)
+    out = torch.zeros(2, cols, dtype=dt, device=DEV)
+    _native.gather_rows(src, bad, out)
+    assert torch.equal(out.cpu(), src[[0, 0]])

@@ -193,3 +193,18 @@ def test_cuda_graph_replay_matches_reference_solver(ns, golden_dir, name, monkey
     for i, k in enumerate(list(g["param_names"])):
         np.testing.assert_allclose(final["state_dict"][k].numpy(), g["param_%02d" % i],
                                    rtol=2e-4, atol=2e-6)
+
+
+def test_device_batch_loader_path_matches_reference_solver(ns, golden_dir, monkeypatch):
+    """Same Problem with its dataset in pinned host memory: the loop uses DeviceBatchLoader
+    (GPU-side row gather + device transform) instead of per-sample __getitem__/collate.  Sample
+    order and arithmetic must not change: per-step losses still match the reference run."""
+    import frl_b200.synthetic as syn
+    g = np.load(os.path.join(golden_dir, "toy_sgd.npz"))
+    orig = syn.make_toy_problem
+    monkeypatch.setattr(syn, "make_toy_problem",
+                        lambda ns_, save_dir, **kw: orig(ns_, save_dir, pinned=True, **kw))
+    _, worker, problem, _ = _solve_and_capture(ns, CONFIGS["toy_sgd"])
+    assert problem.datasets[0].served == []            # the per-sample path was never used
+    rows = np.concatenate([r for _, _, r in worker.loss_history])
+    np.testing.assert_allclose(rows, g["rows"], rtol=1e-5, atol=1e-6)
