@@ -49,6 +49,33 @@ gather_rows_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ 
     }
 }
 
+// Narrow rows (labels, small targets): one UNIT-sized element per thread, grid-stride.
+template <typename U>
+__global__ void __launch_bounds__(kGThreads)
+gather_small_rows_kernel(const U* __restrict__ src, const int64_t* __restrict__ idx, U* __restrict__ dst,
+                         int64_t n_rows, int64_t units_per_row, int64_t src_rows) {
+    const int64_t total = n_rows * units_per_row;
+    for (int64_t u = static_cast<int64_t>(blockIdx.x) * kGThreads + threadIdx.x; u < total;
+         u += static_cast<int64_t>(gridDim.x) * kGThreads) {
+        const int64_t row = u / units_per_row, col = u % units_per_row;
+        int64_t from = __ldg(idx + row);
+        if (from < 0 || from >= src_rows) from = 0;
+        dst[u] = src[from * units_per_row + col];
+    }
+}
+
+template <typename U>
+static void launch_small(const void* src, const int64_t* idx, void* dst, int64_t n_rows, int64_t row_bytes,
+                         int64_t src_rows, int max_blocks, cudaStream_t st) {
+    const int64_t upr = row_bytes / static_cast<int64_t>(sizeof(U));
+    int64_t grid = (n_rows * upr + kGThreads - 1) / kGThreads;
+    const int64_t cap = max_blocks > 0 ? max_blocks : 64;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    gather_small_rows_kernel<U><<<static_cast<int>(grid), kGThreads, 0, st>>>(
+        static_cast<const U*>(src), idx, static_cast<U*>(dst), n_rows, upr, src_rows);
+}
+
 }  // namespace frl
 
 using namespace frl;
@@ -59,12 +86,21 @@ extern "C" int frl_gather_rows(const void* src_mapped, int64_t src_rows, const i
     FRL_REQUIRE(n_rows >= 0 && row_bytes >= 0 && src_rows >= 1, FRL_E_ARG, "frl_gather_rows: sizes");
     if (n_rows == 0 || row_bytes == 0) return 0;
     FRL_REQUIRE(src_mapped && idx_dev && dst, FRL_E_ARG, "frl_gather_rows: null pointer");
-    FRL_REQUIRE(row_bytes % 16 == 0 && aligned16(src_mapped) && aligned16(dst), FRL_E_ALIGN,
-                "frl_gather_rows: rows must be multiples of 16 bytes and 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uintptr_t both = reinterpret_cast<uintptr_t>(src_mapped) | reinterpret_cast<uintptr_t>(dst);
+    if (row_bytes % 16 != 0 || (both & 15u)) {
+        if (row_bytes % 8 == 0 && (both & 7u) == 0)
+            launch_small<uint64_t>(src_mapped, idx_dev, dst, n_rows, row_bytes, src_rows, max_blocks, st);
+        else if (row_bytes % 4 == 0 && (both & 3u) == 0)
+            launch_small<uint32_t>(src_mapped, idx_dev, dst, n_rows, row_bytes, src_rows, max_blocks, st);
+        else
+            launch_small<uint8_t>(src_mapped, idx_dev, dst, n_rows, row_bytes, src_rows, max_blocks, st);
+        return after_launch("frl_gather_rows");
+    }
     const int64_t segs = n_rows * ((row_bytes + kGSegBytes - 1) / kGSegBytes);
     int64_t grid = max_blocks > 0 ? max_blocks : 64;
     if (grid > segs) grid = segs;
-    gather_rows_kernel<<<static_cast<int>(grid), kGThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    gather_rows_kernel<<<static_cast<int>(grid), kGThreads, 0, st>>>(
         static_cast<const uint8_t*>(src_mapped), idx_dev, static_cast<uint8_t*>(dst), n_rows, row_bytes,
         src_rows);
     return after_launch("frl_gather_rows");

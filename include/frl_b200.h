@@ -207,7 +207,8 @@ int frl_nvls_rmsprop(float* p, float* sq, float* buf, const void* mc_g, void* mc
  * dst[i, :] = src[idx[i], :].  Replaces the per-sample __getitem__/collate/H2D sequence of the
  * loop (reference solver_worker.py:462-469): the kernel's PCIe reads are the transfer.
  * src_mapped: host pointer valid on the device (cudaHostAlloc / torch pin_memory); idx_dev:
- * int64 [n_rows] (device or mapped); row_bytes % 16 == 0.  max_blocks <= 0 -> 64 CTAs.
+ * int64 [n_rows] (device or mapped).  Rows that are multiples of 16 bytes take the wide path,
+ * narrower rows (labels) an element-wise one.  max_blocks <= 0 -> 64 CTAs.
  * ---------------------------------------------------------------------------------------- */
 int frl_gather_rows(const void* src_mapped, int64_t src_rows, const int64_t* idx_dev, void* dst,
                     int64_t n_rows, int64_t row_bytes, int max_blocks, void* stream);

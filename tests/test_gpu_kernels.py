@@ -433,7 +433,8 @@ def test_linear_gradients_are_written_into_the_arena(precision):
 # ------------------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("rows,cols,dt", [(1000, 64, torch.float32), (257, 4096, torch.float32),
-                                          (64, 8, torch.int64), (33, 1024, torch.bfloat16)])
+                                          (64, 8, torch.int64), (33, 1024, torch.bfloat16),
+                                          (500, 1, torch.int64), (77, 3, torch.float32), (50, 5, torch.uint8)])
 def test_gather_rows_from_pinned_host_memory(rows, cols, dt):
     src = (torch.randn(rows, cols) * 100).to(dt).pin_memory()
     idx = torch.randint(0, rows, (123,), dtype=torch.int64)
