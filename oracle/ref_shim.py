@@ -55,6 +55,10 @@ def import_reference():
         import unittest.mock
         sys.modules["mock"] = unittest.mock
 
+    # an frl_b200.install_reference_alias() made earlier in this process must not shadow the
+    # real reference
+    for k in [k for k in sys.modules if k == "frldistml" or k.startswith("frldistml.")]:
+        del sys.modules[k]
     root = tempfile.mkdtemp(prefix="frl_ref_shim_")
     os.makedirs(os.path.join(root, "frldistml"))
     open(os.path.join(root, "frldistml", "__init__.py"), "w").close()

@@ -149,10 +149,19 @@ def test_lr_schedules_match_reference_tables(golden_dir):
 
 
 def test_reference_alias_makes_reference_imports_resolve():
-    frl_b200.install_reference_alias()
-    from frldistml.scaffold.sampler import per_node_randperm   # reference tests/test_sampler.py:11
-    from frldistml.scaffold.types import RunOpts
-    assert per_node_randperm is sampler.per_node_randperm and RunOpts is types.RunOpts
+    import sys
+    saved = {k: v for k, v in sys.modules.items() if k == "frldistml" or k.startswith("frldistml.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        frl_b200.install_reference_alias()
+        from frldistml.scaffold.sampler import per_node_randperm   # reference tests/test_sampler.py:11
+        from frldistml.scaffold.types import RunOpts
+        assert per_node_randperm is sampler.per_node_randperm and RunOpts is types.RunOpts
+    finally:       # the oracle shim imports the REAL reference under the same name: leave no alias
+        for k in [k for k in sys.modules if k == "frldistml" or k.startswith("frldistml.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
 
 
 def test_model_helpers():
