@@ -347,16 +347,21 @@ def main_b200(args, rank, local_rank, world):
     # ======================= leg 2: end to end from host buffers =======================
     e2e = None
     if not args.no_e2e:
-        # The dataset (fp32, 16 batches per rank) lives in pinned host memory behind the Problem's
-        # `datasets`; the loop's own DeviceBatchLoader shuffles it, pulls the rows of the next
-        # batch over PCIe (frl_gather_rows on a copy stream) while the current one trains, and runs
-        # the transform on the device (frl_preproc_affine -> bf16).  The criterion kernel's loss
-        # row goes to the pinned loss log and is read by the host 2 steps late.
+        # The dataset (fp32) lives in pinned host memory behind the Problem's `datasets`; the loop's
+        # own DeviceBatchLoader shuffles it (reference sampler machinery), moves the rows of the
+        # next batches to HBM while the current one trains (default: native host gather threads +
+        # one DMA per field; FRL_B200_INPUT_PATH=tma|kernel lets the GPU pull them over PCIe) and
+        # runs the transform on the device (frl_preproc_affine -> bf16).  The criterion kernel's
+        # loss row goes to the pinned loss log and is read by the host 2 steps late.
         from frl_b200.device_loader import DeviceBatchLoader
         from frl_b200 import synthetic as syn
-        n_host = 16 * B
+        # one epoch = every step of this leg (+ slack): epoch boundaries (sampler reshuffle,
+        # pipeline refill) are per-epoch costs, outside the steady-state step being measured
+        n_host_batches = max(32, W + K + 8 + (6 if args.profile else 0))
+        n_host = n_host_batches * B
         host_problem = syn.make_mlp_problem(ns, save_dir, n_train=n_host, width=WIDTH,
-                                            n_classes=N_CLASSES, reg_dim=REG_DIM, depth=DEPTH, pinned=True)
+                                            n_classes=N_CLASSES, reg_dim=REG_DIM, depth=DEPTH,
+                                            pinned=True, fast_fields=True)
         host_ds = host_problem.datasets[0]
         out_dtype = torch.bfloat16 if precision == Precision.BF16 else torch.float32
         loader = DeviceBatchLoader(host_ds, batch_size=B, sampler=None, device=dev, out_dtype=out_dtype)
@@ -392,15 +397,30 @@ def main_b200(args, rank, local_rank, world):
         m1.record()
         barrier()
         e2e_ms = max_over_ranks(m0.elapsed_time(m1))
+        if args.profile and rank == 0:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+                for i in range(6):
+                    step_e2e(W + K + i)
+                torch.cuda.synchronize()
+            prof.export_chrome_trace(args.profile.replace(".json", "") + "_e2e.json")
+            log(prof.key_averages().table(sort_by="cuda_time_total", row_limit=20))
         assert all(x == x for x in seen), "NaN loss in the e2e leg"
         e2e = {"value": world * B * K / (e2e_ms / 1e3), "unit": "samples/s",
                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 * (1 + n_tasks),
-               "ms_per_step": e2e_ms / K,
-               "how": "Problem dataset (fp32) in pinned host memory -> DeviceBatchLoader: sampler "
-                      "indices, rows of the next batch pulled over PCIe by frl_gather_rows on a copy "
-                      "stream (overlapped with the current step), transform + bf16 cast on device -> "
-                      "SolverWorker._pass_one_minibatch; loss row written to pinned host memory by "
-                      "the criterion kernel, read by the host 2 steps late",
+               "ms_per_step": e2e_ms / K, "input_path": loader.path,
+               "input_threads": loader.threads, "input_blocks": loader.blocks,
+               "host_dataset_batches": n_host_batches,
+               "how": "Problem dataset (fp32, %d batches) in pinned host memory -> DeviceBatchLoader: "
+                      "reference sampler indices -> rows of the next batches moved to HBM while the "
+                      "current step runs (%s) -> transform + bf16 cast on device (frl_preproc_affine) "
+                      "-> SolverWorker._pass_one_minibatch; loss row written to pinned host memory "
+                      "by the criterion kernel, read by the host 2 steps late" % (
+                          n_host_batches,
+                          "native host gather threads into pinned staging + one DMA per field"
+                          if loader.path == "host" else
+                          "rows pulled over PCIe by frl_gather_rows%s on a copy stream" % (
+                              "_tma" if loader.path == "tma" else "")),
                "losses_read": len(seen)}
 
     # ======================= CPU baseline (rank 0, N=1) =======================

@@ -59,6 +59,12 @@ SIGNATURES = {
     "frl_colsum_scratch_bytes": (_i64, [_i64, _i64]),
     "frl_colsum": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i, _vp, _vp]),
     "frl_gather_rows": (_i, [_vp, _i64, _vp, _vp, _i64, _i64, _i, _vp]),
+    "frl_gather_rows_tma": (_i, [_vp, _i64, _vp, _vp, _i64, _i64, _i, _vp]),
+    "frl_gather_pool_create": (_vp, [_i]),
+    "frl_gather_pool_destroy": (None, [_vp]),
+    "frl_gather_pool_threads": (_i, [_vp]),
+    "frl_gather_pool_submit": (_i64, [_vp, _vp, _i64, _vp, _vp, _i64, _i64]),
+    "frl_gather_pool_wait": (_i, [_vp, _i64]),
     "frl_nvls_sgd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d, _vp, _i, _i, _vp]),
     "frl_nvls_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d,
                            _i64, _d, _vp, _i, _vp]),
@@ -263,3 +269,52 @@ def gather_rows(src_pinned, idx_dev, dst, max_blocks: int = 64) -> None:
     _check(lib().frl_gather_rows(_ptr(src_pinned), src_pinned.shape[0], _ptr(idx_dev), _ptr(dst),
                                  idx_dev.numel(), row_bytes, max_blocks, _stream()),
            "frl_gather_rows")
+
+
+def _row_bytes(src) -> int:
+    return src[0].numel() * src.element_size() if src.shape[0] else 0
+
+
+def gather_rows_tma(src_pinned, idx_dev, dst, max_blocks: int = 0) -> None:
+    """``gather_rows`` through the SMs' bulk-copy engine (rows must be multiples of 16 bytes)."""
+    assert src_pinned.is_pinned() and src_pinned.is_contiguous() and dst.is_contiguous()
+    _check(lib().frl_gather_rows_tma(_ptr(src_pinned), src_pinned.shape[0], _ptr(idx_dev), _ptr(dst),
+                                     idx_dev.numel(), _row_bytes(src_pinned), max_blocks, _stream()),
+           "frl_gather_rows_tma")
+
+
+class HostGatherPool:
+    """Persistent native worker threads assembling minibatch rows into pinned staging buffers."""
+
+    def __init__(self, n_threads: int) -> None:
+        self._h = lib().frl_gather_pool_create(int(n_threads))
+        if not self._h:
+            raise NativeLibraryError("frl_gather_pool_create failed: "
+                                     + lib().frl_last_error().decode("utf-8", "replace"))
+        self.n_threads = int(lib().frl_gather_pool_threads(self._h))
+
+    def submit(self, src, idx_host, dst_host) -> int:
+        """Queue dst_host[i] = src[idx_host[i]]; returns a ticket for ``wait``."""
+        assert src.is_contiguous() and dst_host.is_contiguous()
+        assert not src.is_cuda and not dst_host.is_cuda and not idx_host.is_cuda
+        assert idx_host.dtype == torch.int64 and idx_host.is_contiguous()
+        assert dst_host.shape[0] >= idx_host.numel()
+        t = int(lib().frl_gather_pool_submit(self._h, _ptr(src), src.shape[0], _ptr(idx_host),
+                                             _ptr(dst_host), idx_host.numel(), _row_bytes(src)))
+        if t < 1:
+            _check(t if t != 0 else -1, "frl_gather_pool_submit")
+        return t
+
+    def wait(self, ticket: int) -> None:
+        _check(lib().frl_gather_pool_wait(self._h, ticket), "frl_gather_pool_wait")
+
+    def close(self) -> None:
+        if self._h:
+            lib().frl_gather_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:                 # noqa: BLE001  (interpreter shutdown)
+            pass

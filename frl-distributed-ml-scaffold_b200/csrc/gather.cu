@@ -64,6 +64,91 @@ gather_small_rows_kernel(const U* __restrict__ src, const int64_t* __restrict__ 
     }
 }
 
+
+// ---- TMA variant -------------------------------------------------------------------------------
+// The copy engine inside every SM (cp.async.bulk, SASS UBLKCP) moves one whole row chunk per
+// instruction: host memory -> shared memory -> HBM, no register staging.  One elected thread per
+// CTA keeps kTStages-1 chunk loads in flight (mbarrier complete_tx) and drains them with bulk
+// stores; PCIe sees long, back-to-back read bursts instead of 128-byte LSU requests.
+constexpr int kTStages = 8;
+constexpr int kTChunk = 16384;           // bytes per stage: 8 x 16 KB = 128 KB dynamic smem
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(32)
+gather_rows_tma_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ idx,
+                       uint8_t* __restrict__ dst, int64_t n_rows, int64_t row_bytes, int64_t src_rows) {
+    extern __shared__ __align__(128) uint8_t tma_buf[];
+    __shared__ uint64_t full[kTStages];
+    if (threadIdx.x != 0) return;
+    for (int s = 0; s < kTStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    const int64_t chunks_per_row = (row_bytes + kTChunk - 1) / kTChunk;
+    const int64_t total = n_rows * chunks_per_row;
+    const int64_t mine = total > blockIdx.x ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    auto issue_load = [&](int64_t k) {
+        const int64_t work = blockIdx.x + k * gridDim.x;
+        const int64_t row = work / chunks_per_row, ch = work % chunks_per_row;
+        int64_t from = __ldg(idx + row);
+        if (from < 0 || from >= src_rows) from = 0;
+        const int64_t base = ch * kTChunk;
+        const uint32_t bytes = static_cast<uint32_t>(row_bytes - base < kTChunk ? row_bytes - base : kTChunk);
+        const int s = static_cast<int>(k % kTStages);
+        mbar_expect_tx(&full[s], bytes);
+        bulk_g2s(tma_buf + static_cast<size_t>(s) * kTChunk, src + from * row_bytes + base, bytes, &full[s]);
+    };
+    int64_t issued = 0;
+    for (; issued < mine && issued < kTStages - 1; ++issued) issue_load(issued);
+    for (int64_t k = 0; k < mine; ++k) {
+        const int s = static_cast<int>(k % kTStages);
+        mbar_wait(&full[s], static_cast<uint32_t>((k / kTStages) & 1));
+        const int64_t work = blockIdx.x + k * gridDim.x;
+        const int64_t row = work / chunks_per_row, ch = work % chunks_per_row;
+        const int64_t base = ch * kTChunk;
+        const uint32_t bytes = static_cast<uint32_t>(row_bytes - base < kTChunk ? row_bytes - base : kTChunk);
+        bulk_s2g(dst + row * row_bytes + base, tma_buf + static_cast<size_t>(s) * kTChunk, bytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (issued < mine) {
+            // the stage about to be refilled was read by the store of chunk k-1
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            issue_load(issued);
+            ++issued;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <typename U>
 static void launch_small(const void* src, const int64_t* idx, void* dst, int64_t n_rows, int64_t row_bytes,
                          int64_t src_rows, int max_blocks, cudaStream_t st) {
@@ -88,8 +173,11 @@ extern "C" int frl_gather_rows(const void* src_mapped, int64_t src_rows, const i
     FRL_REQUIRE(src_mapped && idx_dev && dst, FRL_E_ARG, "frl_gather_rows: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uintptr_t both = reinterpret_cast<uintptr_t>(src_mapped) | reinterpret_cast<uintptr_t>(dst);
-    if (row_bytes % 16 != 0 || (both & 15u)) {
-        if (row_bytes % 8 == 0 && (both & 7u) == 0)
+    if (row_bytes % 16 != 0 || (both & 15u) || row_bytes < 4096) {
+        // narrow rows: one unit per thread across rows (a CTA pass per row would idle most lanes)
+        if (row_bytes % 16 == 0 && (both & 15u) == 0)
+            launch_small<int4>(src_mapped, idx_dev, dst, n_rows, row_bytes, src_rows, max_blocks, st);
+        else if (row_bytes % 8 == 0 && (both & 7u) == 0)
             launch_small<uint64_t>(src_mapped, idx_dev, dst, n_rows, row_bytes, src_rows, max_blocks, st);
         else if (row_bytes % 4 == 0 && (both & 3u) == 0)
             launch_small<uint32_t>(src_mapped, idx_dev, dst, n_rows, row_bytes, src_rows, max_blocks, st);
@@ -104,4 +192,33 @@ extern "C" int frl_gather_rows(const void* src_mapped, int64_t src_rows, const i
         static_cast<const uint8_t*>(src_mapped), idx_dev, static_cast<uint8_t*>(dst), n_rows, row_bytes,
         src_rows);
     return after_launch("frl_gather_rows");
+}
+
+
+// TMA (cp.async.bulk) variant of frl_gather_rows: rows must be multiples of 16 bytes.
+extern "C" int frl_gather_rows_tma(const void* src_mapped, int64_t src_rows, const int64_t* idx_dev,
+                                   void* dst, int64_t n_rows, int64_t row_bytes, int max_blocks,
+                                   void* stream) {
+    FRL_REQUIRE(n_rows >= 0 && row_bytes >= 0 && src_rows >= 1, FRL_E_ARG, "frl_gather_rows_tma: sizes");
+    if (n_rows == 0 || row_bytes == 0) return 0;
+    FRL_REQUIRE(src_mapped && idx_dev && dst, FRL_E_ARG, "frl_gather_rows_tma: null pointer");
+    const uintptr_t both = reinterpret_cast<uintptr_t>(src_mapped) | reinterpret_cast<uintptr_t>(dst);
+    FRL_REQUIRE(row_bytes % 16 == 0 && (both & 15u) == 0, FRL_E_ALIGN,
+                "frl_gather_rows_tma: rows and pointers must be multiples of 16 bytes");
+    static bool attr_set = false;
+    const int smem = kTStages * kTChunk;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gather_rows_tma_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        FRL_REQUIRE(e == cudaSuccess, static_cast<int>(e), "frl_gather_rows_tma: smem attribute: %s",
+                    cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int64_t work = n_rows * ((row_bytes + kTChunk - 1) / kTChunk);
+    int64_t grid = max_blocks > 0 ? max_blocks : sm_count();
+    if (grid > work) grid = work;
+    gather_rows_tma_kernel<<<static_cast<int>(grid), 32, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint8_t*>(src_mapped), idx_dev, static_cast<uint8_t*>(dst), n_rows, row_bytes,
+        src_rows);
+    return after_launch("frl_gather_rows_tma");
 }

@@ -273,13 +273,26 @@ def make_toy_problem(ns, save_dir: str, n_train: int = 512, n_test: int = 128,
                               criterion_kind=criterion_kind, pinned=pinned)
 
 
+def synthetic_fields_fast(n: int, in_dim: int, reg_dim: int, n_classes: int, seed: int
+                          ) -> Dict[str, np.ndarray]:
+    """Same shapes/distributions as ``synthetic_fields`` from torch's (multi-threaded) generator:
+    for the multi-GB host datasets of the benchmark, where numpy's scalar generator takes minutes."""
+    g = torch.Generator().manual_seed(seed)
+    return {"x": torch.randn(n, in_dim, generator=g).numpy(),
+            "y_reg": torch.randn(n, reg_dim, generator=g).numpy(),
+            "y_cls": torch.randint(0, n_classes, (n,), generator=g).numpy()}
+
+
 def make_mlp_problem(ns, save_dir: str, n_train: int = 8192, n_test: int = 0, width: int = 4096,
-                     n_classes: int = 1000, reg_dim: int = 64, depth: int = 3, pinned: bool = False):
+                     n_classes: int = 1000, reg_dim: int = 64, depth: int = 3, pinned: bool = False,
+                     fast_fields: bool = False):
     """Configs 2/3: trunk depth x [Linear(width,width)+ReLU], CE head width->1000 (w 1), MSE
     head width->64 (w 1); x ~ N(0,1)."""
     Reg, Cls = _task_classes(ns)
     tasks = [Cls(width, n_classes, 1.0), Reg(width, reg_dim, 1.0)]
-    fields = [(ns.Split.TRAIN, synthetic_fields(n_train, width, reg_dim, n_classes, 0, False))]
+    train = (synthetic_fields_fast(n_train, width, reg_dim, n_classes, 0) if fast_fields
+             else synthetic_fields(n_train, width, reg_dim, n_classes, 0, False))
+    fields = [(ns.Split.TRAIN, train)]
     if n_test:
         fields.append((ns.Split.TEST, synthetic_fields(n_test, width, reg_dim, n_classes, 1, False)))
     return _problem_class(ns)(tasks, [width] * (depth + 1), fields, save_dir, shift=0.0, scale=1.0,

@@ -212,6 +212,35 @@ int frl_nvls_rmsprop(float* p, float* sq, float* buf, const void* mc_g, void* mc
  * ---------------------------------------------------------------------------------------- */
 int frl_gather_rows(const void* src_mapped, int64_t src_rows, const int64_t* idx_dev, void* dst,
                     int64_t n_rows, int64_t row_bytes, int max_blocks, void* stream);
+/* Same contract, moved by the SMs' bulk-copy engine (cp.async.bulk: host -> shared memory -> HBM,
+ * one elected thread per CTA, 8 x 16 KB stages in flight).  Rows and pointers must be multiples
+ * of 16 bytes.  max_blocks <= 0 -> one CTA per SM. */
+int frl_gather_rows_tma(const void* src_mapped, int64_t src_rows, const int64_t* idx_dev, void* dst,
+                        int64_t n_rows, int64_t row_bytes, int max_blocks, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host gather pool — the host half of the input path (no CUDA calls inside).
+ * Replaces the reference's per-sample __getitem__ + transform + default_collate on the host
+ * (reference solver_worker.py:805-832, transform.py:25-38) with native worker threads that copy
+ * the raw rows of a minibatch, dst[i, :] = src[idx[i], :], into a pinned staging buffer with
+ * non-temporal stores; the caller then moves the staging buffer to HBM with one DMA and runs the
+ * per-sample arithmetic on the device (K5).
+ *   create(n_threads)            -> pool or NULL (frl_last_error)
+ *   submit(...)                  -> ticket >= 1, or a negative FRL_E_* code; returns immediately;
+ *                                   idx is copied, src/dst must stay valid until the job completes;
+ *                                   an index outside [0, src_rows) rejects the whole job
+ *   wait(pool, ticket)           -> blocks until every job up to and including `ticket` is done
+ *                                   and its stores are globally visible (sfence)
+ * Thread-safe; jobs run FIFO.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct frl_gather_pool frl_gather_pool;
+frl_gather_pool* frl_gather_pool_create(int n_threads);
+void frl_gather_pool_destroy(frl_gather_pool* pool);
+int frl_gather_pool_threads(const frl_gather_pool* pool);
+int64_t frl_gather_pool_submit(frl_gather_pool* pool, const void* src_host, int64_t src_rows,
+                               const int64_t* idx_host, void* dst_host, int64_t n_rows,
+                               int64_t row_bytes);
+int frl_gather_pool_wait(frl_gather_pool* pool, int64_t ticket);
 
 #ifdef __cplusplus
 }

@@ -447,3 +447,30 @@ def test_gather_rows_from_pinned_host_memory(rows, cols, dt):
     out = torch.zeros(2, cols, dtype=dt, device=DEV)
     _native.gather_rows(src, bad, out)
     assert torch.equal(out.cpu(), src[[0, 0]])
+
+
+@pytest.mark.parametrize("rows,cols,dt,blocks", [(1000, 4096, torch.float32, 0), (257, 4096, torch.float32, 3),
+                                                 (64, 8, torch.int64, 1), (33, 1024, torch.bfloat16, 2),
+                                                 (300, 4096 + 8, torch.float32, 4), (40, 3 * 224 * 224, torch.uint8, 5),
+                                                 (9, 20000, torch.float32, 7)])
+def test_tma_gather_rows_matches_index_select(rows, cols, dt, blocks):
+    """cp.async.bulk variant: rows longer than one 16 KB stage are chunked, tails are partial
+    chunks, more stages than work items, every grid size."""
+    src = (torch.randn(rows, cols) * 100).to(dt).pin_memory()
+    n = 211
+    idx = torch.randint(0, rows, (n,), dtype=torch.int64)
+    dst = torch.zeros(n, cols, dtype=dt, device=DEV)
+    _native.gather_rows_tma(src, idx.to(DEV), dst, max_blocks=blocks)
+    torch.cuda.synchronize()
+    assert torch.equal(dst.cpu(), src[idx])
+    bad = torch.tensor([rows + 5, -1], dtype=torch.int64, device=DEV)
+    out = torch.zeros(2, cols, dtype=dt, device=DEV)
+    _native.gather_rows_tma(src, bad, out)
+    assert torch.equal(out.cpu(), src[[0, 0]])
+
+
+def test_tma_gather_rejects_rows_that_are_not_multiples_of_16_bytes():
+    src = torch.zeros(10, 3).pin_memory()
+    with pytest.raises(_native.NativeLibraryError):
+        _native.gather_rows_tma(src, torch.zeros(2, dtype=torch.int64, device=DEV),
+                                torch.zeros(2, 3, device=DEV))

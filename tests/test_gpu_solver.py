@@ -195,11 +195,14 @@ def test_cuda_graph_replay_matches_reference_solver(ns, golden_dir, name, monkey
                                    rtol=2e-4, atol=2e-6)
 
 
-def test_device_batch_loader_path_matches_reference_solver(ns, golden_dir, monkeypatch):
+@pytest.mark.parametrize("path", ["host", "tma", "kernel"])
+def test_device_batch_loader_path_matches_reference_solver(ns, golden_dir, monkeypatch, path):
     """Same Problem with its dataset in pinned host memory: the loop uses DeviceBatchLoader
-    (GPU-side row gather + device transform) instead of per-sample __getitem__/collate.  Sample
-    order and arithmetic must not change: per-step losses still match the reference run."""
+    (native host gather + DMA, or GPU-side row gather, + device transform) instead of per-sample
+    __getitem__/collate.  Sample order and arithmetic must not change: per-step losses still
+    match the reference run."""
     import frl_b200.synthetic as syn
+    monkeypatch.setenv("FRL_B200_INPUT_PATH", path)
     g = np.load(os.path.join(golden_dir, "toy_sgd.npz"))
     orig = syn.make_toy_problem
     monkeypatch.setattr(syn, "make_toy_problem",

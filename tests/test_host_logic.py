@@ -199,3 +199,45 @@ def test_two_rank_pipeline_equals_global_batch_training(tmp_path, algo, clip):
         ref_opt.step()
     for a, b in zip(r0, ref.parameters()):
         np.testing.assert_allclose(a.numpy(), b.detach().numpy(), rtol=2e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# host gather pool (native threads; no GPU involved)
+# ------------------------------------------------------------------------------------------------
+
+def test_host_gather_pool_matches_index_select_and_orders_tickets():
+    from frl_b200 import _native
+    pool = _native.HostGatherPool(3)
+    assert pool.n_threads == 3
+    src = torch.randn(5000, 1024)
+    jobs = []
+    for k in range(6):
+        idx = torch.randperm(5000)[:700 + k].contiguous()
+        dst = torch.zeros(800, 1024)
+        jobs.append((pool.submit(src, idx, dst), idx, dst))
+    assert [t for t, _, _ in jobs] == list(range(1, 7))
+    pool.wait(jobs[-1][0])                    # FIFO: waiting for the last covers all
+    for _, idx, dst in jobs:
+        assert torch.equal(dst[:len(idx)], src[idx])
+        assert torch.count_nonzero(dst[len(idx):]) == 0
+    # narrow rows (labels), repeated indices, unaligned row sizes
+    lab = torch.arange(1000, dtype=torch.int64)
+    out = torch.zeros(6, dtype=torch.int64)
+    pool.wait(pool.submit(lab, torch.tensor([5, 999, 0, 3, 3, 3]), out))
+    assert out.tolist() == [5, 999, 0, 3, 3, 3]
+    odd = torch.randn(100, 7)
+    out = torch.zeros(9, 7)
+    idx = torch.randint(0, 100, (9,))
+    pool.wait(pool.submit(odd, idx, out))
+    assert torch.equal(out, odd[idx])
+    # empty job completes; a bad index rejects the whole job and nothing is written
+    pool.wait(pool.submit(lab, torch.zeros(0, dtype=torch.int64), out))
+    keep = out.clone()
+    with pytest.raises(_native.NativeLibraryError):
+        pool.submit(odd, torch.tensor([1, 100]), out)
+    with pytest.raises(_native.NativeLibraryError):
+        pool.submit(odd, torch.tensor([-1]), out)
+    assert torch.equal(out, keep)
+    with pytest.raises(_native.NativeLibraryError):
+        pool.wait(10_000)                     # never issued
+    pool.close()
