@@ -429,6 +429,16 @@ def main_b200(args, rank, local_rank, world):
         res = time_cpu_reference(args.algo, args.cpu_batch, args.cpu_steps, 1)
         cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    nv = worker.pipeline.nvls
+    if world == 1:
+        grad_sync_desc = "none (1 GPU)"
+    elif nv is not None:
+        grad_sync_desc = ("fused per-bucket NVLS kernel over NVSwitch multicast (multimem.ld_reduce of the "
+                          "bf16 grads + sharded update + multimem.st of the new weights), %d buckets, "
+                          "%d CTAs, barriers %s" % (len(worker.pipeline.buckets), nv.max_blocks,
+                                                    "as separate 1-CTA launches" if nv.flags & 1 else "in-kernel"))
+    else:
+        grad_sync_desc = "NCCL all-reduce in place on bf16 arena buckets + fused update per bucket"
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": total_ms / K, "step_p50_ms": statistics.median(step_ms),
@@ -442,7 +452,7 @@ def main_b200(args, rank, local_rank, world):
                                         "optimizer state" if precision == Precision.BF16 else "fp32",
                            "l2": "no flush needed: each step streams the 54.7M-element arena "
                                  "(>= 1.1 GB) and 4 rotating input batches, far larger than the 126 MB L2",
-                           "grad_allreduce": "NCCL in place on bf16 arena buckets" if world > 1 else "none (1 GPU)"},
+                           "grad_allreduce": grad_sync_desc},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks.summary(), "final_loss": float(losses[-1])}
         print(json.dumps(line), flush=True)

@@ -65,11 +65,12 @@ SIGNATURES = {
     "frl_gather_pool_threads": (_i, [_vp]),
     "frl_gather_pool_submit": (_i64, [_vp, _vp, _i64, _vp, _vp, _i64, _i64]),
     "frl_gather_pool_wait": (_i, [_vp, _i64]),
-    "frl_nvls_sgd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d, _vp, _i, _i, _vp]),
+    "frl_nvls_sgd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d, _vp, _i, _i, _i, _vp]),
     "frl_nvls_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d,
-                           _i64, _d, _vp, _i, _vp]),
+                           _i64, _d, _vp, _i, _i, _vp]),
     "frl_nvls_rmsprop": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d, _d,
-                              _vp, _i, _vp]),
+                              _vp, _i, _i, _vp]),
+    "frl_nvls_barrier": (_i, [_vp, _i, _i, _i, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -239,7 +240,7 @@ def nvls_sgd(p, buf, mc_g, mc_out, n, link, *, lr, mu, dampening, wd, grad_scale
              g_dtype, dyn=None) -> None:
     _check(lib().frl_nvls_sgd(_ptr(p), _ptr(buf), mc_g, mc_out, n, link.rank, link.world,
                               link.pads_dev, link.pad_base, _ptr(link.scratch), link.max_blocks, lr, mu, dampening, wd,
-                              grad_scale, _ptr(dyn), int(first_step), g_dtype, _stream()),
+                              grad_scale, _ptr(dyn), int(first_step), g_dtype, link.flags, _stream()),
            "frl_nvls_sgd")
 
 
@@ -247,7 +248,7 @@ def nvls_adam(p, m, v, vmax, mc_g, mc_out, n, link, *, lr, beta1, beta2, eps, wd
               g_dtype, dyn=None) -> None:
     _check(lib().frl_nvls_adam(_ptr(p), _ptr(m), _ptr(v), _ptr(vmax), mc_g, mc_out, n, link.rank,
                                link.world, link.pads_dev, link.pad_base, _ptr(link.scratch), link.max_blocks, lr, beta1,
-                               beta2, eps, wd, step, grad_scale, _ptr(dyn), g_dtype, _stream()),
+                               beta2, eps, wd, step, grad_scale, _ptr(dyn), g_dtype, link.flags, _stream()),
            "frl_nvls_adam")
 
 
@@ -255,8 +256,16 @@ def nvls_rmsprop(p, sq, buf, mc_g, mc_out, n, link, *, lr, alpha, eps, wd, mu, g
                  dyn=None) -> None:
     _check(lib().frl_nvls_rmsprop(_ptr(p), _ptr(sq), _ptr(buf), mc_g, mc_out, n, link.rank,
                                   link.world, link.pads_dev, link.pad_base, _ptr(link.scratch), link.max_blocks, lr,
-                                  alpha, eps, wd, mu, grad_scale, _ptr(dyn), g_dtype, _stream()),
+                                  alpha, eps, wd, mu, grad_scale, _ptr(dyn), g_dtype, link.flags, _stream()),
            "frl_nvls_rmsprop")
+
+
+NVLS_EXTERNAL_SYNC = 1
+
+
+def nvls_barrier(link, slot: int) -> None:
+    _check(lib().frl_nvls_barrier(link.pads_dev, link.rank, link.world, slot, _stream()),
+           "frl_nvls_barrier")
 
 
 # ---- K8 -------------------------------------------------------------------------------------

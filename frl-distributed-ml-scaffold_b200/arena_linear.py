@@ -40,6 +40,8 @@ class _ArenaLinearFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
         site = ctx.site
+        # dX first: marking the weight's slot ready may launch the bucket's update on the side
+        # stream, and that update overwrites the very weight dX = dY W reads
         dx = dy.matmul(weight) if ctx.needs_input_grad[0] else None
         dy2 = dy.reshape(-1, dy.shape[-1])
         x2 = x.reshape(-1, x.shape[-1])

@@ -96,6 +96,7 @@ struct NvlsCommon {
     uint32_t* const* pads;
     uint32_t* local;
     int rank, world, pad_base;
+    int sync_inside;      // 0: the caller brackets the launch with frl_nvls_barrier
     int64_t n;            // bucket elements
     float gscale;
     const float* dyn;
@@ -113,7 +114,7 @@ nvls_update_bf16(float* __restrict__ p_, float* __restrict__ s0_, float* __restr
                  float* __restrict__ s2_, const __nv_bfloat16* mc_g, __nv_bfloat16* mc_lp,
                  Rule rule, NvlsCommon c) {
     if (c.dyn) rule.patch(c.dyn);
-    kernel_entry_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
+    if (c.sync_inside) kernel_entry_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
     const int64_t per = ((c.n + c.world - 1) / c.world + 7) / 8 * 8;
     const int64_t lo = static_cast<int64_t>(c.rank) * per;
     int64_t hi = lo + per;
@@ -162,7 +163,8 @@ nvls_update_bf16(float* __restrict__ p_, float* __restrict__ s0_, float* __restr
             }
         }
     }
-    kernel_exit_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
+    if (c.sync_inside) kernel_exit_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
+    else __threadfence_system();                                  // my multimem stores before the grid ends
 }
 
 // FP32 mode: fp32 gradients in, parameters ARE the master: multicast the new fp32 weights.
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(kNThreads)
 nvls_update_f32(const float* __restrict__ p_, float* __restrict__ s0_, float* __restrict__ s1_,
                 float* __restrict__ s2_, const float* mc_g, float* mc_p, Rule rule, NvlsCommon c) {
     if (c.dyn) rule.patch(c.dyn);
-    kernel_entry_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
+    if (c.sync_inside) kernel_entry_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
     const int64_t per = ((c.n + c.world - 1) / c.world + 7) / 8 * 8;
     const int64_t lo = static_cast<int64_t>(c.rank) * per;
     int64_t hi = lo + per;
@@ -208,14 +210,15 @@ nvls_update_f32(const float* __restrict__ p_, float* __restrict__ s0_, float* __
             if (NS > 2) st_stream(reinterpret_cast<f32x4*>(s2_ + e), a2);
         }
     }
-    kernel_exit_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
+    if (c.sync_inside) kernel_exit_barrier(c.pads, c.rank, c.world, c.pad_base, c.local);
+    else __threadfence_system();                                  // my multimem stores before the grid ends
 }
 
 template <typename Rule, int NS>
 static int launch_nvls(const Rule& rule, float* p, float* s0, float* s1, float* s2, const void* mc_g,
                        void* mc_out, int64_t n, int rank, int world, void* const* pads, int pad_base,
                        void* local_scratch, int max_blocks, double gscale, const float* dyn, int g_dtype,
-                       void* stream, const char* name) {
+                       int flags, void* stream, const char* name) {
     FRL_REQUIRE(p && mc_g && mc_out && pads, FRL_E_ARG, "%s: null pointer", name);
     FRL_REQUIRE(world >= 2 && world <= 32 && rank >= 0 && rank < world, FRL_E_ARG, "%s: rank/world", name);
     FRL_REQUIRE(n >= 0 && n % 8 == 0, FRL_E_ARG, "%s: bucket size must be a multiple of 8 elements", name);
@@ -225,7 +228,7 @@ static int launch_nvls(const Rule& rule, float* p, float* s0, float* s1, float* 
     FRL_REQUIRE(max_blocks >= 1 && max_blocks <= 1024 && local_scratch, FRL_E_ARG,
                 "%s: max_blocks in 1..1024 and a local scratch are required", name);
     NvlsCommon c{reinterpret_cast<uint32_t* const*>(pads), static_cast<uint32_t*>(local_scratch), rank,
-                 world, pad_base, n,
+                 world, pad_base, (flags & FRL_NVLS_EXTERNAL_SYNC) ? 0 : 1, n,
                  static_cast<float>(gscale), dyn};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // the grid must be identical on every rank: it depends on arguments only
@@ -245,43 +248,64 @@ using namespace frl;
 extern "C" int frl_nvls_sgd(float* p, float* buf, const void* mc_g, void* mc_out, int64_t n, int rank,
                             int world, void* const* signal_pads_dev, int pad_base, void* local_scratch,
                             int max_blocks, double lr, double mu, double dampening, double wd, double grad_scale,
-                            const float* dyn, int first_step, int g_dtype, void* stream) {
+                            const float* dyn, int first_step, int g_dtype, int flags, void* stream) {
     FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_nvls_sgd: momentum needs buf");
     const SgdRule r = make_sgd_rule(lr, mu, dampening, wd, first_step);
     if (mu != 0.0)
         return launch_nvls<SgdRule, 1>(r, p, buf, nullptr, nullptr, mc_g, mc_out, n, rank, world,
-                                       signal_pads_dev, pad_base, local_scratch, max_blocks, grad_scale, dyn, g_dtype,
-                                       stream, "frl_nvls_sgd");
+                                       signal_pads_dev, pad_base, local_scratch, max_blocks, grad_scale, dyn, g_dtype, flags, stream, "frl_nvls_sgd");
     return launch_nvls<SgdRule, 0>(r, p, nullptr, nullptr, nullptr, mc_g, mc_out, n, rank, world,
-                                   signal_pads_dev, pad_base, local_scratch, max_blocks, grad_scale, dyn, g_dtype, stream,
+                                   signal_pads_dev, pad_base, local_scratch, max_blocks, grad_scale, dyn, g_dtype, flags, stream,
                                    "frl_nvls_sgd");
 }
 
 extern "C" int frl_nvls_adam(float* p, float* m, float* v, float* vmax, const void* mc_g, void* mc_out,
                              int64_t n, int rank, int world, void* const* signal_pads_dev, int pad_base,
                              void* local_scratch, int max_blocks, double lr, double beta1, double beta2, double eps, double wd,
-                             int64_t step, double grad_scale, const float* dyn, int g_dtype, void* stream) {
+                             int64_t step, double grad_scale, const float* dyn, int g_dtype, int flags, void* stream) {
     FRL_REQUIRE(m && v && step >= 1, FRL_E_ARG, "frl_nvls_adam: state/step");
     if (vmax)
         return launch_nvls<AdamRule<true>, 3>(make_adam_rule<true>(lr, beta1, beta2, eps, wd, step), p, m, v,
                                               vmax, mc_g, mc_out, n, rank, world, signal_pads_dev, pad_base,
-                                              local_scratch, max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_adam");
+                                              local_scratch, max_blocks, grad_scale, dyn, g_dtype, flags, stream, "frl_nvls_adam");
     return launch_nvls<AdamRule<false>, 2>(make_adam_rule<false>(lr, beta1, beta2, eps, wd, step), p, m, v,
                                            nullptr, mc_g, mc_out, n, rank, world, signal_pads_dev, pad_base,
-                                           local_scratch, max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_adam");
+                                           local_scratch, max_blocks, grad_scale, dyn, g_dtype, flags, stream, "frl_nvls_adam");
 }
 
 extern "C" int frl_nvls_rmsprop(float* p, float* sq, float* buf, const void* mc_g, void* mc_out, int64_t n,
                                 int rank, int world, void* const* signal_pads_dev, int pad_base,
                                 void* local_scratch, int max_blocks, double lr, double alpha, double eps, double wd, double mu,
-                                double grad_scale, const float* dyn, int g_dtype, void* stream) {
+                                double grad_scale, const float* dyn, int g_dtype, int flags, void* stream) {
     FRL_REQUIRE(sq, FRL_E_ARG, "frl_nvls_rmsprop: null sq");
     FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_nvls_rmsprop: momentum needs buf");
     if (mu != 0.0)
         return launch_nvls<RmspropRule<true>, 2>(make_rmsprop_rule<true>(lr, alpha, eps, wd, mu), p, sq, buf,
                                                  nullptr, mc_g, mc_out, n, rank, world, signal_pads_dev, pad_base,
-                                                 local_scratch, max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_rmsprop");
+                                                 local_scratch, max_blocks, grad_scale, dyn, g_dtype, flags, stream, "frl_nvls_rmsprop");
     return launch_nvls<RmspropRule<false>, 1>(make_rmsprop_rule<false>(lr, alpha, eps, wd, mu), p, sq, nullptr,
                                               nullptr, mc_g, mc_out, n, rank, world, signal_pads_dev, pad_base,
-                                              local_scratch, max_blocks, grad_scale, dyn, g_dtype, stream, "frl_nvls_rmsprop");
+                                              local_scratch, max_blocks, grad_scale, dyn, g_dtype, flags, stream, "frl_nvls_rmsprop");
+}
+
+
+// Cross-GPU rendezvous as its own 1-CTA launch.  With FRL_NVLS_EXTERNAL_SYNC the bucket sequence on
+// the side stream is  barrier(slot 0) -> frl_nvls_* -> barrier(slot 1): while a rank waits for
+// slower peers only one warp is resident, instead of a whole grid of spinning CTAs that keeps the
+// backward GEMMs of this rank off the SMs; the update kernel itself then never waits.
+namespace frl {
+__global__ void __launch_bounds__(32)
+nvls_barrier_kernel(uint32_t* const* pads, int rank, int world, int base) {
+    meet_peers_block0(pads, rank, world, base);
+}
+}  // namespace frl
+
+extern "C" int frl_nvls_barrier(void* const* signal_pads_dev, int rank, int world, int pad_slot,
+                                void* stream) {
+    FRL_REQUIRE(signal_pads_dev, FRL_E_ARG, "frl_nvls_barrier: null pads");
+    FRL_REQUIRE(world >= 2 && world <= 32 && rank >= 0 && rank < world, FRL_E_ARG, "frl_nvls_barrier: rank/world");
+    FRL_REQUIRE(pad_slot >= 0 && pad_slot < 8, FRL_E_ARG, "frl_nvls_barrier: pad_slot in 0..7");
+    frl::nvls_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<uint32_t* const*>(signal_pads_dev), rank, world, pad_slot * 32);
+    return frl::after_launch("frl_nvls_barrier");
 }

@@ -15,7 +15,7 @@ arithmetic runs once per batch on the device (``frl_preproc_affine``).
 
 Three ways to move the rows (``FRL_B200_INPUT_PATH``):
 
-``host`` (default)  native worker threads (``frl_gather_pool_*``) copy the rows of batch *k+2* into
+``host``            native worker threads (``frl_gather_pool_*``) copy the rows of batch *k+2* into
                     a pinned staging buffer, the copy engine moves batch *k+1* to HBM as one
                     contiguous DMA per field, the SMs see nothing of it;
 ``tma``             ``frl_gather_rows_tma``: a few CTAs pull the rows over PCIe with
@@ -24,7 +24,9 @@ Three ways to move the rows (``FRL_B200_INPUT_PATH``):
 
 Measured on B200 (round 1): every path reaches PCIe speed (51-55 GB/s, 1.2-1.3 ms for a 67 MB
 batch) when run alone, but CTAs that occupy SMs for that long slow the step's cluster-scheduled
-GEMMs by ~35 %, so the DMA path is the default.
+GEMMs by ~35 %, so ``host`` is the default on up to 2 GPUs per node.  It costs host DRAM 3x the PCIe
+payload, which 8 ranks cannot afford (4.3 ms/step vs 2.0 for the SM paths): ``auto`` switches to
+``kernel`` there, whose CTAs are small enough to share SMs with the GEMM CTAs.
 """
 from collections import deque
 from typing import Dict, Iterator, List, Optional, Tuple
@@ -62,6 +64,26 @@ def supports_device_batches(dataset) -> bool:
             and isinstance(getattr(dataset, "device_transform", None), DeviceBatchTransform))
 
 
+def _local_world() -> int:
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "0") or 0)
+    if local_world < 1:
+        local_world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            local_world = max(1, min(torch.distributed.get_world_size(), torch.cuda.device_count() or 1))
+    return local_world
+
+
+def default_input_path() -> str:
+    """``host`` while the ranks of this node are few enough for host DRAM to carry the staging
+    copy (3x the PCIe payload: gather read + staging write + DMA read), else ``kernel`` (1x).
+    Measured, 67 MB fp32 batches, ms/step end to end: 1 x B200 host 1.47 | kernel (16 CTAs) 1.53 |
+    kernel (8) 1.69 | tma (2 CTAs) 2.08 | tma (8) 2.85; 4 x B200 host 2.47 | tma 2.03;
+    8 x B200 host 4.3 | tma 2.0 (the box's aggregate H2D rate, ~270 GB/s, is the floor there).
+    The LSU kernel's CTAs (256 threads, no shared memory) fit beside the GEMM CTAs on an SM; the
+    TMA kernel's 128 KB of staging does not, so each of its CTAs takes an SM from the GEMMs."""
+    return "host" if _local_world() <= 2 else "kernel"
+
+
 def default_gather_threads() -> int:
     """Worker threads for the host gather: this rank's share of the cores it may run on."""
     env = os.environ.get("FRL_B200_INPUT_THREADS")
@@ -71,11 +93,7 @@ def default_gather_threads() -> int:
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 4
-    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "0") or 0)
-    if local_world < 1:
-        local_world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            local_world = max(1, min(torch.distributed.get_world_size(), torch.cuda.device_count() or 1))
+    local_world = _local_world()
     share = min(avail, (os.cpu_count() or avail) // local_world)
     return max(1, min(share - 2, 24))
 
@@ -102,10 +120,12 @@ class DeviceBatchLoader:
                 raise ValueError(f"field {name!r} must be a contiguous pinned host tensor")
         # high priority: the next batch's transfer should start as soon as it is submitted
         self._copy_stream = torch.cuda.Stream(device=device, priority=-1)
-        self.path = path or os.environ.get("FRL_B200_INPUT_PATH", "host")
+        self.path = path or os.environ.get("FRL_B200_INPUT_PATH", "auto")
+        if self.path == "auto":
+            self.path = default_input_path()
         if self.path not in ("host", "tma", "kernel"):
             raise ValueError(f"unknown input path {self.path!r}")
-        self.blocks = int(os.environ.get("FRL_B200_INPUT_BLOCKS", "4"))
+        self.blocks = int(os.environ.get("FRL_B200_INPUT_BLOCKS", "2" if self.path == "tma" else "16"))
         self._slots = []
         for _ in range(self.depth):
             slot = {name: torch.empty((batch_size,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)

@@ -103,7 +103,12 @@ class FusedArenaOptimizer(torch.optim.Optimizer):
     # -- fused all-reduce + update + broadcast (K7) ------------------------------------------------
     def apply_range_nvls(self, lo: int, hi: int, *, grad_scale: float) -> None:
         if hi > lo:
+            split = bool(self.nvls.flags & KERNELS.NVLS_EXTERNAL_SYNC)
+            if split:
+                KERNELS.nvls_barrier(self.nvls, 0)     # every rank's bucket gradients are written
             self._launch_nvls(lo, hi, grad_scale)
+            if split:
+                KERNELS.nvls_barrier(self.nvls, 1)     # every replica has every shard
 
     def _launch_nvls(self, lo: int, hi: int, grad_scale: float) -> None:
         raise NotImplementedError

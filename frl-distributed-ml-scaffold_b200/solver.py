@@ -280,13 +280,22 @@ class Solver:
         nvls_link = None
         if symm_alloc is not None:
             from .symm import make_link
+            # grid of the fused NVLS step: each rank streams 1/world of a bucket, and every CTA it
+            # parks on an SM while backward runs costs the cluster-scheduled GEMMs a wave, so the
+            # grid shrinks with the world size.  Measured, ms/step with 24 MiB buckets:
+            #   8 x B200: 16 CTAs 1.12 | 32: 1.17 | 74: 1.25 | 148: 1.40
+            #   4 x B200:  8 CTAs 1.42 | 16: 1.16 | 37: 1.17 | 74: 1.25
+            #   2 x B200: 32 CTAs 1.48 | 74: 1.26 | 148: 1.31   (half of every bucket per rank)
+            default_blocks = 74 if args.world_size <= 2 else 16
             nvls_link = make_link(symm_alloc, arena.grad,
                                   arena.lp if arena.lp is not None else arena.master,
-                                  max_blocks=int(os.environ.get("FRL_B200_NVLS_BLOCKS", "148")))
+                                  max_blocks=int(os.environ.get("FRL_B200_NVLS_BLOCKS", default_blocks)))
         pipeline = GradBucketPipeline(
             arena, optimizer, world_size=args.world_size, clip_norm=run_opts.optim.gradientClip,
             nvls_link=nvls_link,
-            bucket_cap_mb=float(os.environ.get("FRL_B200_BUCKET_MB", "48")), first_bucket_mb=None,
+            bucket_cap_mb=float(os.environ.get("FRL_B200_BUCKET_MB",
+                                               "24" if nvls_link is not None else "48")),
+            first_bucket_mb=None,
             eager_update=os.environ.get("FRL_B200_EAGER_UPDATE",
                                         "1" if args.world_size > 1 else "0") != "0")
         # GradNorm differentiates through the layers' backward (create_graph=True) and debugGrad

@@ -19,7 +19,7 @@ logger = logging.getLogger(__name__)
 class NvlsLink:
     """What the K7 launches need besides the bucket pointers."""
     __slots__ = ("rank", "world", "pads_dev", "pad_base", "max_blocks", "mc_grad", "mc_out",
-                 "grad_esz", "out_esz", "handles", "scratch")
+                 "grad_esz", "out_esz", "handles", "scratch", "flags")
 
     def __init__(self):
         self.handles = []
@@ -84,6 +84,9 @@ def make_link(alloc: SymmetricAllocator, grad: torch.Tensor, out: torch.Tensor,
     link.mc_grad, link.mc_out = hg.multicast_ptr, ho.multicast_ptr
     link.grad_esz, link.out_esz = grad.element_size(), out.element_size()
     link.handles = [hg, ho]
+    # barriers inside the update kernel (default: measured best with the small grids used) or as
+    # separate 1-CTA launches (wins when the grid is large and ranks arrive skewed)
+    link.flags = 1 if os.environ.get("FRL_B200_NVLS_SPLIT_SYNC", "0") != "0" else 0
     if link.mc_grad == 0 or link.mc_out == 0:
         raise RuntimeError("no multicast mapping")
     return link

@@ -7,6 +7,9 @@ as ``frldistml.scaffold`` (oracle only) to run the very same Problem on the refe
 
 * ``make_toy_problem``  — config 1: 64-d input, 2x128 trunk, MSE head (w=0.5) + CE head (w=2).
 * ``make_mlp_problem``  — configs 2/3: 4096-d input, 3x4096 trunk, CE head (1000) + MSE head (64).
+* ``make_resnet_problem`` — config 4 (torchvision resnet18 trunk + one CE head, 11 689 512
+  parameters) and config 5 (resnet50 trunk + heads 2048->{1000 CE, 100 CE, 10 MSE, 4 MSE},
+  25 790 618 parameters) on synthetic 3xHxW images.
 """
 import importlib
 from types import SimpleNamespace
@@ -201,9 +204,10 @@ def _problem_class(ns):
 
         def __init__(self, tasks, trunk_dims: Sequence[int], datasets_fields, save_dir: str,
                      shift: float, scale: float, criterion_kind: str = "parallel",
-                     pinned: bool = False) -> None:
+                     pinned: bool = False, base_factory=None) -> None:
             self._tasks = tasks
             self._trunk_dims = list(trunk_dims)
+            self._base_factory = base_factory
             self._save_dir = save_dir
             self._criterion_kind = criterion_kind
             self.transform = CenteringTransform(tasks, shift, scale)
@@ -230,6 +234,8 @@ def _problem_class(ns):
             return None
 
         def get_model_base(self) -> nn.Module:
+            if self._base_factory is not None:
+                return self._base_factory()
             layers: List[nn.Module] = [ns.model.ListSelect(sel_index=0, num_elements=1)]
             for d_in, d_out in zip(self._trunk_dims[:-1], self._trunk_dims[1:]):
                 layers += [nn.Linear(d_in, d_out), nn.ReLU()]
@@ -297,3 +303,45 @@ def make_mlp_problem(ns, save_dir: str, n_train: int = 8192, n_test: int = 0, wi
         fields.append((ns.Split.TEST, synthetic_fields(n_test, width, reg_dim, n_classes, 1, False)))
     return _problem_class(ns)(tasks, [width] * (depth + 1), fields, save_dir, shift=0.0, scale=1.0,
                               pinned=pinned)
+
+
+RESNET_CONFIGS = {
+    # name: (torchvision arch, [(kind, out_dim, field, task name)])
+    "resnet18": ("resnet18", [("cls", 1000, "y_cls", "cls")]),
+    "resnet50x4": ("resnet50", [("cls", 1000, "y_cls", "cls1000"), ("cls", 100, "y_cls2", "cls100"),
+                                ("reg", 10, "y_reg", "reg10"), ("reg", 4, "y_reg2", "reg4")]),
+}
+
+
+def resnet_fields(n: int, image: int, heads, seed: int) -> Dict[str, np.ndarray]:
+    g = torch.Generator().manual_seed(seed)
+    fields = {"x": torch.randn(n, 3, image, image, generator=g).numpy()}
+    for kind, dim, field, _ in heads:
+        if kind == "cls":
+            fields[field] = torch.randint(0, dim, (n,), generator=g).numpy()
+        else:
+            fields[field] = torch.randn(n, dim, generator=g).numpy()
+    return fields
+
+
+def make_resnet_problem(ns, save_dir: str, config: str = "resnet18", image: int = 224,
+                        n_train: int = 64, n_test: int = 0, pinned: bool = False):
+    """Configs 4/5: a torchvision ResNet trunk (its ``fc`` removed) behind
+    ``ListSelect`` and one ``nn.Linear`` head per task; x ~ N(0,1) of shape [3, image, image]."""
+    import torchvision
+    arch, heads = RESNET_CONFIGS[config]
+    feat = {"resnet18": 512, "resnet50": 2048}[arch]
+    Reg, Cls = _task_classes(ns)
+    tasks = [(Cls if kind == "cls" else Reg)(feat, dim, 1.0, field=field, name=name)
+             for kind, dim, field, name in heads]
+
+    def base_factory() -> nn.Module:
+        net = getattr(torchvision.models, arch)(weights=None)
+        net.fc = nn.Identity()
+        return nn.Sequential(ns.model.ListSelect(sel_index=0, num_elements=1), net)
+
+    fields = [(ns.Split.TRAIN, resnet_fields(n_train, image, heads, 0))]
+    if n_test:
+        fields.append((ns.Split.TEST, resnet_fields(n_test, image, heads, 1)))
+    return _problem_class(ns)(tasks, [], fields, save_dir, shift=0.0, scale=1.0, pinned=pinned,
+                              base_factory=base_factory)

@@ -184,23 +184,31 @@ int frl_colsum(const void* x, int x_dtype, int64_t rows, int64_t cols, void* out
  *   signal_pads_dev    device array [world] of pointers to each rank's uint32 signal pad;
  *                      slots [pad_base, pad_base + 64) are used
  *   local_scratch      rank-local uint32[8 + max_blocks], zero-initialised once
- *   max_blocks         grid size (1..1024, all blocks must be co-resident)
+ *   max_blocks         grid size (1..1024; with in-kernel barriers all blocks must be co-resident)
+ *   flags              0: the kernel carries both barriers itself.
+ *                      FRL_NVLS_EXTERNAL_SYNC: no barrier inside; the caller issues, on the same
+ *                      stream, frl_nvls_barrier(slot 0) before and frl_nvls_barrier(slot 1) after.
+ *                      A rank that waits for slower peers then holds one warp instead of a grid
+ *                      of spinning CTAs (which would keep its own backward GEMMs off the SMs).
  * n must be a multiple of 8; launch order must be identical on all ranks.
  * ---------------------------------------------------------------------------------------- */
+enum { FRL_NVLS_EXTERNAL_SYNC = 1 };
+/* 1-CTA cross-GPU rendezvous over the signal pads (slots [32*pad_slot, 32*pad_slot + world)). */
+int frl_nvls_barrier(void* const* signal_pads_dev, int rank, int world, int pad_slot, void* stream);
 int frl_nvls_sgd(float* p, float* buf, const void* mc_g, void* mc_out, int64_t n, int rank,
                  int world, void* const* signal_pads_dev, int pad_base, void* local_scratch,
                  int max_blocks, double lr, double mu, double dampening, double wd, double grad_scale,
-                 const float* dyn, int first_step, int g_dtype, void* stream);
+                 const float* dyn, int first_step, int g_dtype, int flags, void* stream);
 int frl_nvls_adam(float* p, float* m, float* v, float* vmax, const void* mc_g, void* mc_out,
                   int64_t n, int rank, int world, void* const* signal_pads_dev, int pad_base,
                   void* local_scratch, int max_blocks, double lr, double beta1, double beta2,
                   double eps, double wd,
-                  int64_t step, double grad_scale, const float* dyn, int g_dtype, void* stream);
+                  int64_t step, double grad_scale, const float* dyn, int g_dtype, int flags, void* stream);
 int frl_nvls_rmsprop(float* p, float* sq, float* buf, const void* mc_g, void* mc_out, int64_t n,
                      int rank, int world, void* const* signal_pads_dev, int pad_base,
                      void* local_scratch, int max_blocks, double lr, double alpha, double eps,
                      double wd, double mu,
-                     double grad_scale, const float* dyn, int g_dtype, void* stream);
+                     double grad_scale, const float* dyn, int g_dtype, int flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K8 — gather the rows of a minibatch from a pinned, device-mapped host dataset into HBM:

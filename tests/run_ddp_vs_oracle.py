@@ -34,9 +34,10 @@ def main():
     alloc = try_make_allocator(dev, world)
     if rank == 0:
         print("NVLS_AVAILABLE", alloc is not None, flush=True)
+    # (algo, clip, nvls): nvls True = barriers as separate launches (default), "inkernel" = inside K7
     combos = [("sgd", 0.0, False), ("adam", 0.0, False), ("rmsprop", 0.0, False), ("sgd", 0.05, False)]
     if alloc is not None:
-        combos += [("sgd", 0.0, True), ("adam", 0.0, True), ("rmsprop", 0.0, True)]
+        combos += [("sgd", 0.0, True), ("adam", 0.0, True), ("rmsprop", 0.0, True), ("sgd", 0.0, "inkernel")]
     nccl_result = {}            # algo -> (weights, optimizer state) of the NCCL + K2 run
     for algo, clip, nvls in combos:
         torch.manual_seed(123 + rank)                 # different init per rank: broadcast must fix
@@ -48,9 +49,11 @@ def main():
         lr = 0.002 if algo == "rmsprop" else 0.02
         opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm(algo), lr=lr))
         link = make_link(alloc, arena.grad, arena.master, max_blocks=8) if nvls else None
+        if link is not None:
+            link.flags = 0 if nvls == "inkernel" else 1
         pipe = grad_sync.GradBucketPipeline(arena, opt, world_size=world, clip_norm=clip,
                                             bucket_cap_mb=0.02, first_bucket_mb=0.005, nvls_link=link)
-        assert (pipe.nvls is not None) == nvls
+        assert (pipe.nvls is not None) == bool(nvls)
         pipe.broadcast_parameters(0)
         assert len(pipe.buckets) >= 3
         g = torch.Generator().manual_seed(7)
@@ -104,10 +107,19 @@ def main():
             nccl_result[algo] = (mine.clone(), state.clone())
         if nvls and rank == 0:
             w_ref, s_ref = nccl_result[algo]
-            torch.testing.assert_close(mine, w_ref, rtol=2e-5, atol=2e-7)
-            torch.testing.assert_close(state, s_ref, rtol=2e-5, atol=1e-9)
+            # a sum of `world` terms in another order differs by <= (world-1) eps sum|g_i|: the
+            # bound scales with the magnitude of the terms, not of a (possibly cancelling) result
+            # (at world 2 both orders give the same bits).  Adam / RMSprop then divide by sqrt(v):
+            # a last-bit change of a gradient moves a weight by a visible fraction of lr where v
+            # is tiny, so their bound is the oracle bound above, 10x tighter.
+            eps = float(torch.finfo(torch.float32).eps)
+            wtol = {"sgd": dict(rtol=2e-5, atol=2e-7 * max(1, world // 2)),
+                    "adam": dict(rtol=1e-4, atol=5e-6), "rmsprop": dict(rtol=2e-4, atol=3e-5)}[algo]
+            torch.testing.assert_close(mine, w_ref, **wtol)
+            torch.testing.assert_close(state, s_ref, rtol=2e-5 if algo == "sgd" else 1e-4,
+                                       atol=max(1e-9, 4 * world * eps * float(s_ref.abs().max())))
         if rank == 0:
-            print("DDP_PARITY_OK", algo, clip, "nvls" if nvls else "nccl", "world", world, flush=True)
+            print("DDP_PARITY_OK", algo, clip, ("nvls-" + str(nvls)) if nvls else "nccl", "world", world, flush=True)
         pipe.remove_hooks()
         dist.barrier()
     dist.destroy_process_group()

@@ -177,7 +177,7 @@ def test_multi_gpu_pipeline_matches_oracle(tmp_path):
                           "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
                           "29533", script], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("DDP_PARITY_OK") == (7 if "NVLS_AVAILABLE True" in out.stdout else 4)
+    assert out.stdout.count("DDP_PARITY_OK") == (8 if "NVLS_AVAILABLE True" in out.stdout else 4)
 
 
 @pytest.mark.parametrize("name", ["toy_sgd", "toy_adam_clip", "toy_uncertainty"])
