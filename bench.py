@@ -344,84 +344,98 @@ def main_b200(args, rank, local_rank, world):
             log(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25))
     barrier()
 
-    # ======================= leg 2: end to end from host buffers =======================
+    # ======================= leg 2: end to end through the public loop =======================
     e2e = None
     if not args.no_e2e:
-        # The dataset (fp32) lives in pinned host memory behind the Problem's `datasets`; the loop's
-        # own DeviceBatchLoader shuffles it (reference sampler machinery), moves the rows of the
-        # next batches to HBM while the current one trains (default: native host gather threads +
-        # one DMA per field; FRL_B200_INPUT_PATH=tma|kernel lets the GPU pull them over PCIe) and
-        # runs the transform on the device (frl_preproc_affine -> bf16).  The criterion kernel's
-        # loss row goes to the pinned loss log and is read by the host 2 steps late.
+        # What a user's Solver.solve() runs per epoch: SolverWorker._pass_one_epoch over the
+        # Problem's own dataset.  The dataset (fp32) lives in pinned HOST memory behind
+        # `problem.datasets`; the loop's DeviceBatchLoader shuffles it with the reference's sampler
+        # machinery, moves the rows of the next batches to HBM while the current one trains
+        # (FRL_B200_INPUT_PATH: native host gather threads + one DMA per field, or GPU-pulled over
+        # PCIe) and runs the transform on the device (frl_preproc_affine -> bf16).  Inside the
+        # timed region, every step: H2D of that step's inputs, the step, the loss row landing in
+        # pinned host memory (read by the host 2 steps late for the NaN guard), and the loop's
+        # bookkeeping — retained batches, per-sample metrics of the Problem's
+        # compute_batch_metrics hook read back every metricAmortizationSchedule (10) steps, epoch
+        # summary.  One epoch of K steps is timed, after one warm-up epoch over the same loader.
         from frl_b200.device_loader import DeviceBatchLoader
         from frl_b200 import synthetic as syn
-        # one epoch = every step of this leg (+ slack): epoch boundaries (sampler reshuffle,
-        # pipeline refill) are per-epoch costs, outside the steady-state step being measured
-        n_host_batches = max(32, W + K + 8 + (6 if args.profile else 0))
-        n_host = n_host_batches * B
+        from frl_b200.types import Mode
+
+        class LocalShardSampler(torch.utils.data.Sampler):
+            """world > 1: every rank owns a node-local shard of the dataset and reshuffles it
+            per epoch (the ScaffoldSampler contract — set_epoch, seeded permutation — on local
+            indices; a global index space would need world x the pinned memory per rank)."""
+
+            def __init__(self, n, seed):
+                self.n, self.seed, self.epoch = n, seed, 0
+
+            def set_epoch(self, epoch):
+                self.epoch = epoch
+
+            def __len__(self):
+                return self.n
+
+            def __iter__(self):
+                g = torch.Generator().manual_seed(self.seed + self.epoch)
+                return iter(torch.randperm(self.n, generator=g).tolist())
+
+        L = K if K <= 128 else K // ((K + 127) // 128)        # steps per epoch
+        n_epochs_timed = max(1, K // L)
+        n_host = L * B
         host_problem = syn.make_mlp_problem(ns, save_dir, n_train=n_host, width=WIDTH,
                                             n_classes=N_CLASSES, reg_dim=REG_DIM, depth=DEPTH,
                                             pinned=True, fast_fields=True)
         host_ds = host_problem.datasets[0]
         out_dtype = torch.bfloat16 if precision == Precision.BF16 else torch.float32
-        loader = DeviceBatchLoader(host_ds, batch_size=B, sampler=None, device=dev, out_dtype=out_dtype)
+        loader = DeviceBatchLoader(host_ds, batch_size=B, device=dev, out_dtype=out_dtype,
+                                   sampler=LocalShardSampler(n_host, 1000 * rank) if world > 1 else None)
+        loaders = {t.Split.TRAIN: loader}
         h2d_bytes = loader.h2d_bytes_per_batch
-        stream_iter = [iter(loader)]
-
-        def next_batch():
-            try:
-                return next(stream_iter[0])
-            except StopIteration:
-                stream_iter[0] = iter(loader)          # next epoch: reshuffle
-                return next(stream_iter[0])
-
-        seen = []
-
-        def step_e2e(i):
-            data, target, _meta = next_batch()
-            worker.criterion.set_step_sink(log_ring.row(i), log_ring.nan_flag)
-            worker._pass_one_minibatch(i, t.Split.TRAIN, data, target)
-            log_ring.mark(i)
-            if i >= 2:                          # device -> host: the loss row the kernel wrote
-                log_ring.wait(i - 2)
-                seen.append(float(log_ring.rows[(i - 2) % log_ring.capacity, 0]))
-
-        for i in range(W):
-            step_e2e(i)
+        worker.cur_epoch = 1
+        worker._pass_one_epoch(host_problem, loaders, Mode.TRAIN)        # warm-up epoch (graph capture)
         barrier()
-        seen.clear()
         m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches_e0 = _native.launch_count() + graph_step.REPLAYED_LAUNCHES
         m0.record()
-        for i in range(K):
-            step_e2e(W + i)
+        for ep in range(n_epochs_timed):
+            worker.cur_epoch = 2 + ep
+            stats = worker._pass_one_epoch(host_problem, loaders, Mode.TRAIN)
         m1.record()
         barrier()
+        e2e_launches = _native.launch_count() + graph_step.REPLAYED_LAUNCHES - launches_e0
+        e2e_steps = n_epochs_timed * L
         e2e_ms = max_over_ranks(m0.elapsed_time(m1))
+        ep_losses = stats[t.Split.TRAIN].losses
+        assert all(v == v for v in ep_losses.values()), "NaN loss in the e2e leg"
         if args.profile and rank == 0:
             from torch.profiler import ProfilerActivity, profile
             with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-                for i in range(6):
-                    step_e2e(W + K + i)
+                worker.cur_epoch += 1
+                worker._pass_one_epoch(host_problem, loaders, Mode.TRAIN)
                 torch.cuda.synchronize()
             prof.export_chrome_trace(args.profile.replace(".json", "") + "_e2e.json")
             log(prof.key_averages().table(sort_by="cuda_time_total", row_limit=20))
-        assert all(x == x for x in seen), "NaN loss in the e2e leg"
-        e2e = {"value": world * B * K / (e2e_ms / 1e3), "unit": "samples/s",
-               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 * (1 + n_tasks),
-               "ms_per_step": e2e_ms / K, "input_path": loader.path,
+        n_metrics = len(stats[t.Split.TRAIN].metrics)
+        e2e = {"value": world * B * e2e_steps / (e2e_ms / 1e3), "unit": "samples/s",
+               "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": 4 * (1 + n_tasks) + 4 * n_metrics * B,
+               "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "input_path": loader.path,
                "input_threads": loader.threads, "input_blocks": loader.blocks,
-               "host_dataset_batches": n_host_batches,
-               "how": "Problem dataset (fp32, %d batches) in pinned host memory -> DeviceBatchLoader: "
-                      "reference sampler indices -> rows of the next batches moved to HBM while the "
-                      "current step runs (%s) -> transform + bf16 cast on device (frl_preproc_affine) "
-                      "-> SolverWorker._pass_one_minibatch; loss row written to pinned host memory "
-                      "by the criterion kernel, read by the host 2 steps late" % (
-                          n_host_batches,
-                          "native host gather threads into pinned staging + one DMA per field"
+               "gpu_launches": e2e_launches,
+               "epoch_losses": {k: float(v) for k, v in ep_losses.items()},
+               "how": "SolverWorker._pass_one_epoch (the loop Solver.solve runs per epoch) over the "
+                      "Problem's dataset (fp32, %d batches) in pinned host memory: reference sampler "
+                      "indices -> DeviceBatchLoader moves the rows of the next batches to HBM while "
+                      "the current step runs (%s) -> transform + bf16 cast on device "
+                      "(frl_preproc_affine) -> _pass_one_minibatch (CUDA-graph replay) -> loss row "
+                      "written to pinned host memory by the criterion kernel, read 2 steps late; "
+                      "includes the loop's retained-batch bookkeeping, the Problem's per-sample "
+                      "metric hook every 10 steps (D2H) and the epoch summary" % (
+                          L, "native host gather threads into pinned staging + one DMA per field"
                           if loader.path == "host" else
                           "rows pulled over PCIe by frl_gather_rows%s on a copy stream" % (
-                              "_tma" if loader.path == "tma" else "")),
-               "losses_read": len(seen)}
+                              "_tma" if loader.path == "tma" else ""))}
 
     # ======================= CPU baseline (rank 0, N=1) =======================
     cpu = None

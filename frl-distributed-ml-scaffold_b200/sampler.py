@@ -37,23 +37,32 @@ class ScaffoldSampler(torch.utils.data.distributed.DistributedSampler):
         self._node_idx = node_idx
         self._node_count = node_count
 
-    def rank_indices(self) -> List[int]:
+    def rank_index_tensor(self) -> torch.Tensor:
+        """This rank's sample ids of the current epoch as an int64 tensor — what ``__iter__``
+        yields, without materialising ``len(dataset)`` Python ints (the batched input path
+        consumes it directly)."""
         gen = torch.Generator()
         gen.manual_seed(self.epoch)
         n = len(self.dataset)
         if self._shuffle_type == ShuffleType.PER_NODE_RANDPERM:
             ranks_per_node = self.num_replicas // self._node_count
-            node_order = per_node_randperm(n, node_idx=self._node_idx,
-                                           node_count=self._node_count, generator=gen)
-            return node_order[self.rank % ranks_per_node:: ranks_per_node]
+            chunk = math.ceil(n / self._node_count)
+            first = self._node_idx * chunk
+            have = min(n - first, chunk)
+            order = torch.randperm(have, generator=gen) + chunk * self._node_idx
+            order = torch.cat([order, order[: chunk - have]])
+            return order[self.rank % ranks_per_node:: ranks_per_node].contiguous()
         if self._shuffle_type != ShuffleType.RANDPERM:
             raise ValueError("Unhandled shuffle type %s", self._shuffle_type)
-        order = torch.randperm(n, generator=gen).tolist() if self.shuffle else list(range(n))
-        order += order[: self.total_size - len(order)]        # pad with the head
+        order = torch.randperm(n, generator=gen) if self.shuffle else torch.arange(n)
+        order = torch.cat([order, order[: self.total_size - n]])          # pad with the head
         assert len(order) == self.total_size
-        mine = order[self.rank: self.total_size: self.num_replicas]
+        mine = order[self.rank: self.total_size: self.num_replicas].contiguous()
         assert len(mine) == self.num_samples
         return mine
+
+    def rank_indices(self) -> List[int]:
+        return self.rank_index_tensor().tolist()
 
     def __iter__(self) -> Iterator[int]:
         return iter(self.rank_indices())

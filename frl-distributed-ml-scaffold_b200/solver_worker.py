@@ -15,8 +15,12 @@ host with the device:
   always False, reference solver_worker.py:829);
 * one watchdog thread per split is kicked per step instead of spawning a Timer per step.
 """
+import bisect
 import heapq
 import io
+import os
+import queue
+import threading
 import itertools
 import json
 import logging
@@ -164,6 +168,57 @@ class LossLog:
             ev.synchronize()
 
 
+class _MetricWorker:
+    """One background thread + one CUDA stream that fold retained minibatches into per-sample
+    metrics.  The Problem's ``compute_batch_metrics`` hook returns host arrays, i.e. it ends in a
+    device-to-host read; called from the training thread (as the reference does every
+    ``metricAmortizationSchedule`` steps, solver_worker.py:286-312) that read drains the whole
+    launch pipeline — about one step of idle GPU per window at B200 step times.  Here the read
+    blocks only this thread; jobs run FIFO, so per-sample metrics keep their order."""
+
+    def __init__(self, device: torch.device) -> None:
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self._jobs: "queue.Queue" = queue.Queue()
+        self._error: Optional[BaseException] = None
+        self._thread = threading.Thread(target=self._run, name="frl-metrics", daemon=True)
+        self._thread.start()
+
+    def _run(self) -> None:
+        torch.cuda.set_device(self.device)
+        while True:
+            job = self._jobs.get()
+            try:
+                if job is None:
+                    return
+                fn, ready = job
+                if self._error is None:
+                    with torch.no_grad(), torch.cuda.stream(self.stream):
+                        self.stream.wait_event(ready)
+                        fn()
+                    self.stream.synchronize()       # before the window's tensors are released
+            except BaseException as e:              # noqa: BLE001  (re-raised in the loop's thread)
+                self._error = e
+            finally:
+                self._jobs.task_done()
+
+    def submit(self, fn, ready: "torch.cuda.Event") -> None:
+        self.raise_pending()
+        self._jobs.put((fn, ready))
+
+    def drain(self) -> None:
+        self._jobs.join()
+        self.raise_pending()
+
+    def raise_pending(self) -> None:
+        if self._error is not None:
+            err, self._error = self._error, None
+            raise err
+
+    def close(self) -> None:
+        self._jobs.put(None)
+
+
 class SamplerState:
     """Keeps the last few minibatches on the device and folds them into per-sample metrics,
     a random sample set and the worst-k samples (reference solver_worker.py:189-374)."""
@@ -187,6 +242,9 @@ class SamplerState:
         self._targets: List[List[Tuple[torch.Tensor, ...]]] = []
         self._outputs: List[List[torch.Tensor]] = []
         self._data_metric: DefaultDict[str, list] = defaultdict(list)
+        self._runner: Optional[_MetricWorker] = None
+        if device.type == "cuda" and os.environ.get("FRL_B200_ASYNC_METRICS", "1") != "0":
+            self._runner = _MetricWorker(device)
 
     @staticmethod
     def _cat_metas(metas: List[RawMetas]) -> RawMetas:
@@ -207,37 +265,70 @@ class SamplerState:
         self._outputs.append([t.detach() for t in outputs])
         self._targets.append([tuple(t.detach() for t in head) for head in targets])
 
-    @staticmethod
-    def _one(i, data, target, output, meta, sample_metric) -> SingleSample:
+    def _one(self, i, data_batches, starts, target, output, meta, sample_metric) -> SingleSample:
+        # the inputs of the retained minibatches are never concatenated (at batch 4096 that is
+        # a 0.3 GB copy per amortisation window for at most a handful of picked samples): find
+        # the minibatch sample ``i`` of the window came from and index into it
+        b = bisect.bisect_right(starts, i) - 1
+        j = i - starts[b]
         return SingleSample(
-            data=[t[i].cpu() for t in data],
+            data=[t[j].cpu() for t in data_batches[b]],
             target=[tuple(t[i].cpu() for t in head) for head in target],
             meta={k: None if v is None else v[i] for k, v in meta._asdict().items()},
             output=[t[i].float().cpu() for t in output],
             metric={k: v[i] for k, v in sample_metric.items()})
 
     def compute_metrics(self) -> None:
+        """Fold the retained minibatches (a 'window') into the split's metrics.  On CUDA the
+        fold runs on the metric thread/stream and this returns at once; ``finish()`` joins."""
         if not self._data:
             return
-        meta = self._problem.refine_batch_meta(self._cat_metas(self._metas))
-        n_heads = len(self._outputs[0])
-        target = [tuple(torch.cat([t[h][j] for t in self._targets])
-                        for j in range(len(self._targets[0][h]))) for h in range(n_heads)]
-        output = [torch.cat([o[h] for o in self._outputs]) for h in range(n_heads)]
+        window = (self._metas, self._data, self._outputs, self._targets)
+        self._metas, self._data, self._outputs, self._targets = [], [], [], []
+        if self._runner is None:
+            self._fold(*window)
+            return
+        ready = torch.cuda.Event()
+        ready.record()                       # everything the window holds has been enqueued
+        self._runner.submit(lambda: self._fold(*window), ready)
+
+    def __enter__(self) -> "SamplerState":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        if self._runner is not None:         # the loop raised before finish(): stop the thread
+            self._runner.close()
+            self._runner = None
+
+    def finish(self) -> None:
+        """All windows folded (re-raises what a fold raised); call before reading results."""
+        if self._runner is not None:
+            self._runner.drain()
+            self._runner.close()
+            self._runner = None
+
+    def _fold(self, metas, data_batches, outputs, targets) -> None:
+        meta = self._problem.refine_batch_meta(self._cat_metas(metas))
+        n_heads = len(outputs[0])
+        target = [tuple(torch.cat([t[h][j] for t in targets])
+                        for j in range(len(targets[0][h]))) for h in range(n_heads)]
+        output = [torch.cat([o[h] for o in outputs]) for h in range(n_heads)]
         output = [o.float() if o.dtype == torch.bfloat16 else o for o in output]
-        data = [torch.cat([d[i] for d in self._data]) for i in range(len(self._data[0]))]
-        n_group = len(data[0])
+        sizes = [len(d[0]) for d in data_batches]
+        starts = [0] + list(itertools.accumulate(sizes))[:-1]
+        n_group = sum(sizes)
 
         sample_metric = self._problem.compute_batch_metrics(
             meta=meta, target=target, output=output, device=self._device)
         if sample_metric is not None:
             for k, v in sample_metric.items():
-                self._data_metric[k] += list(v)
+                self._data_metric[k].append(np.asarray(v))     # joined once, at the epoch's end
 
         if self._n_vis > 0 and sample_metric is not None:
             base = self._cur_samples
             for i in sorted(j - base for j in self._random_indices if base <= j < base + n_group):
-                self._random_samples.append(self._one(i, data, target, output, meta, sample_metric))
+                self._random_samples.append(
+                    self._one(i, data_batches, starts, target, output, meta, sample_metric))
             # worst-k: only the k most extreme samples of this group can enter the heap
             scores = np.asarray(sample_metric[self._rankable_metric], dtype=np.float64).copy()
             valid = np.ones(n_group, dtype=bool) if self._allow_non_positive_definite else scores >= 0
@@ -250,13 +341,12 @@ class SamplerState:
             for i in cand:
                 score = float(scores[i])
                 if len(self._worst_samples) < self._n_vis:
-                    heapq.heappush(self._worst_samples,
-                                   (score, self._one(int(i), data, target, output, meta, sample_metric)))
+                    heapq.heappush(self._worst_samples, (score, self._one(
+                        int(i), data_batches, starts, target, output, meta, sample_metric)))
                 elif score > self._worst_samples[0][0]:
-                    heapq.heappushpop(self._worst_samples,
-                                      (score, self._one(int(i), data, target, output, meta, sample_metric)))
+                    heapq.heappushpop(self._worst_samples, (score, self._one(
+                        int(i), data_batches, starts, target, output, meta, sample_metric)))
         self._cur_samples += n_group
-        self._metas, self._data, self._outputs, self._targets = [], [], [], []
 
     @property
     def n_samples(self) -> int:
@@ -272,7 +362,27 @@ class SamplerState:
 
     @property
     def data_metric(self) -> Dict[str, np.ndarray]:
-        return self._data_metric
+        """Per-sample metrics of the whole split, one array per metric (the reference grows
+        Python lists of scalars per sample, solver_worker.py:318-319; same length and order)."""
+        return {k: (np.concatenate([np.atleast_1d(a) for a in v]) if v else np.zeros(0))
+                for k, v in self._data_metric.items()}
+
+
+def _planned_order(sampler, accessor) -> List[int]:
+    """``list(iter(sampler))`` as the reference hands it to its dataset cache — or, when the
+    accessor is the null one that ignores the order, just that call's side effect on the global
+    RNG: a stock ``RandomSampler`` draws one int64 seed and shuffles with a private generator, a
+    ``ScaffoldSampler`` seeds a private generator with the epoch.  Materialising the order is
+    O(len(dataset)) Python objects per split per epoch, comparable to the epoch's whole step
+    time on a B200."""
+    if isinstance(accessor, NullAccessor):
+        if (type(sampler) is torch.utils.data.RandomSampler and not sampler.replacement
+                and sampler.generator is None and sampler._num_samples is None):
+            torch.empty((), dtype=torch.int64).random_()
+            return []
+        if isinstance(sampler, ScaffoldSampler):
+            return []
+    return list(iter(sampler))
 
 
 class SolverWorker:
@@ -337,7 +447,7 @@ class SolverWorker:
                 loader.sampler.set_epoch(self.cur_epoch)
             # the planned order goes to the (null) cache accessor; drawing it also keeps the
             # global RNG stream identical to the reference's (solver_worker.py:431)
-            self.accessor.set_sequence_indices(list(iter(loader.sampler)))
+            self.accessor.set_sequence_indices(_planned_order(loader.sampler, self.accessor))
             loader.dataset.set_accessor(self.accessor)
             logger.info("Starting split %s" % data_type.name)
 
@@ -356,7 +466,7 @@ class SolverWorker:
             checked = 0
             batch_start = time.time()
 
-            with StepWatchdog(self.run_opts.minibatchTimeoutMs) as dog:
+            with StepWatchdog(self.run_opts.minibatchTimeoutMs) as dog, sampler_state:
                 for minibatch_idx, (data, target, raw_meta) in enumerate(loader):
                     dog.kick()
                     data = [t if t.is_cuda else t.to(self.device, non_blocking=True) for t in data]
@@ -406,6 +516,7 @@ class SolverWorker:
                     self._raise_if_nan(log, checked, data_type)
                     checked += 1
                 sampler_state.compute_metrics()
+                sampler_state.finish()
             timer.epoch.update(time.time() - epoch_start)
 
             per_step = log.rows[:n_batches].numpy()

@@ -207,7 +207,18 @@ def test_device_batch_loader_path_matches_reference_solver(ns, golden_dir, monke
     orig = syn.make_toy_problem
     monkeypatch.setattr(syn, "make_toy_problem",
                         lambda ns_, save_dir, **kw: orig(ns_, save_dir, pinned=True, **kw))
-    _, worker, problem, _ = _solve_and_capture(ns, CONFIGS["toy_sgd"])
+    # depth 2 < metricAmortizationSchedule: retained targets must survive slot recycling
+    summaries, worker, problem, _ = _solve_and_capture(ns, CONFIGS["toy_sgd"], metricAmortizationSchedule=5)
     assert problem.datasets[0].served == []            # the per-sample path was never used
     rows = np.concatenate([r for _, _, r in worker.loss_history])
     np.testing.assert_allclose(rows, g["rows"], rtol=1e-5, atol=1e-6)
+    # the amortised per-sample metrics (Problem.compute_batch_metrics on retained batches) equal
+    # those of the per-sample DataLoader path
+    monkeypatch.setattr(syn, "make_toy_problem", orig)
+    plain, _, _, _ = _solve_and_capture(ns, CONFIGS["toy_sgd"], metricAmortizationSchedule=5)
+    for split in (ns.Split.TRAIN, ns.Split.TEST):
+        want = plain[-1].performance[split].metrics
+        got = summaries[-1].performance[split].metrics
+        assert set(got) == set(want) and len(want) >= 2
+        for k in want:
+            assert got[k] == pytest.approx(want[k], rel=1e-5, abs=1e-7), (split, k)

@@ -241,3 +241,44 @@ def test_host_gather_pool_matches_index_select_and_orders_tickets():
     with pytest.raises(_native.NativeLibraryError):
         pool.wait(10_000)                     # never issued
     pool.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# index stream of the batched input path: same batches, same global-RNG consumption as the
+# reference's enumerate(DataLoader(shuffle=True)) / list(iter(sampler))
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n,batch", [(1000, 64), (64, 64), (65, 64), (7, 3), (1, 4)])
+def test_fast_index_stream_equals_dataloader_stream_and_rng_draws(n, batch):
+    import torch.utils.data as tud
+    from frl_b200.device_loader import DeviceBatchLoader, _IndexOnly, _collate_indices
+    torch.manual_seed(5)
+    ld = tud.DataLoader(_IndexOnly(n), batch_size=batch, shuffle=True, num_workers=0,
+                        collate_fn=_collate_indices)
+    want = [b.clone() for b in ld]
+    rng_after = torch.get_rng_state()
+
+    class Shell:                       # the three attributes _index_batches reads
+        sampler, batch_size, _index_loader = ld.sampler, batch, ld
+
+    torch.manual_seed(5)
+    got = list(DeviceBatchLoader._index_batches(Shell))
+    assert len(got) == len(want) and all(torch.equal(a, b) for a, b in zip(got, want))
+    assert torch.equal(torch.get_rng_state(), rng_after)
+
+
+def test_planned_order_for_the_null_accessor_only_draws_the_seed():
+    import torch.utils.data as tud
+    from frl_b200.solver_worker import _planned_order
+    from frl_b200.storage_layers.dataset import NullAccessor
+    sampler = tud.RandomSampler(range(1234))
+    torch.manual_seed(9)
+    full = list(iter(sampler))
+    rng_after = torch.get_rng_state()
+    torch.manual_seed(9)
+    assert _planned_order(sampler, NullAccessor()) == []
+    assert torch.equal(torch.get_rng_state(), rng_after)
+    torch.manual_seed(9)
+    assert _planned_order(sampler, object()) == full           # a real cache accessor gets the order
+    seq = tud.SequentialSampler(range(5))
+    assert _planned_order(seq, NullAccessor()) == [0, 1, 2, 3, 4]
