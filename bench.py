@@ -315,12 +315,31 @@ def main_b200(args, rank, local_rank, world):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = bpp * upd_elems / (sum(upd_ms) / 1e3) / 1e9 if upd_ms else None
     traffic = None
     tpath = os.path.join(REPO, "profiles", "k2_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("%s_%s" % (args.algo, args.precision))
-    roofline = {"bound": "hbm", "kernel": "frl::update_kernel (fused grad-bucket + optimizer, K2)",
+    nv_link = worker.pipeline.nvls
+    kernel_name = "frl::update_kernel (fused grad-bucket + optimizer, K2)"
+    nvlink = None
+    if nv_link is not None and upd_ms:
+        # K7: per bucket element this GPU's HBM serves its gradient copy to the switch (2 B, bf16),
+        # receives the new shadow weight (2 B) and streams master + state for its 1/world shard
+        state_bytes = bpp - 2 - 2 if args.precision == "bf16" else bpp - 4
+        bpp = (4 if args.precision == "bf16" else 8) + state_bytes / world
+        kernel_name = ("frl::nvls_update (K7: multimem.ld_reduce + sharded update + multimem.st; "
+                       "launch time includes its two cross-GPU barriers)")
+        g_b = 2 if args.precision == "bf16" else 4
+        link_bytes = upd_elems * g_b * (1.0 + 1.0 / world)          # per direction, per GPU
+        nvlink = {"bytes_per_direction_per_launch": link_bytes / len(upd_ms),
+                  "achieved": link_bytes / (sum(upd_ms) / 1e3) / 1e9, "peak": 770.0, "unit": "GB/s",
+                  "peak_source": "measured peer copy per direction (B200_PROFILING.md); 900 nominal",
+                  "note": "NVLink 5 per-direction payload of the fused step: out = own gradient copy "
+                          "read by the switch + multicast of the shard's new weights, in = reduced shard "
+                          "+ every shard's new weights; this, the barriers and the SMs left over by the "
+                          "overlapped backward GEMMs bound K7, not HBM"}
+    achieved = bpp * upd_elems / (sum(upd_ms) / 1e3) / 1e9 if upd_ms else None
+    roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_param": bpp, "timed_by": roofline_from,
@@ -329,6 +348,11 @@ def main_b200(args, rank, local_rank, world):
                 "update_ms_per_step": (sum(upd_ms) / len(upd_ms)) * (arena.numel / (upd_elems / len(upd_ms))) if upd_ms else None}
     if roofline["update_ms_per_step"]:
         roofline["share_of_step"] = roofline["update_ms_per_step"] / (total_ms / K)
+    if nvlink is not None:
+        roofline["nvlink"] = nvlink
+        roofline["traffic"] = None
+        roofline["note"] = ("multi-GPU: the update is sharded 1/world per rank and overlapped with "
+                            "backward; the single-GPU run carries the HBM roofline of the update kernel (K2)")
 
     if args.profile:
         # every rank runs the steps (collectives!); only rank 0 records
@@ -362,23 +386,24 @@ def main_b200(args, rank, local_rank, world):
         from frl_b200 import synthetic as syn
         from frl_b200.types import Mode
 
-        class LocalShardSampler(torch.utils.data.Sampler):
+        from frl_b200.sampler import ScaffoldSampler
+
+        class LocalShardSampler(ScaffoldSampler):
             """world > 1: every rank owns a node-local shard of the dataset and reshuffles it
-            per epoch (the ScaffoldSampler contract — set_epoch, seeded permutation — on local
-            indices; a global index space would need world x the pinned memory per rank)."""
+            per epoch (the ScaffoldSampler contract — set_epoch, permutation from a generator
+            seeded per epoch — on local indices; a global index space would need world x the
+            pinned memory per rank)."""
 
-            def __init__(self, n, seed):
+            def __init__(self, n, seed):                    # no DistributedSampler bookkeeping
+                torch.utils.data.Sampler.__init__(self)
                 self.n, self.seed, self.epoch = n, seed, 0
-
-            def set_epoch(self, epoch):
-                self.epoch = epoch
 
             def __len__(self):
                 return self.n
 
-            def __iter__(self):
+            def rank_index_tensor(self):
                 g = torch.Generator().manual_seed(self.seed + self.epoch)
-                return iter(torch.randperm(self.n, generator=g).tolist())
+                return torch.randperm(self.n, generator=g)
 
         L = K if K <= 128 else K // ((K + 127) // 128)        # steps per epoch
         n_epochs_timed = max(1, K // L)

@@ -24,8 +24,9 @@ Three ways to move the rows (``FRL_B200_INPUT_PATH``):
 
 Measured on B200 (round 1): every path reaches PCIe speed (51-55 GB/s, 1.2-1.3 ms for a 67 MB
 batch) when run alone, but CTAs that occupy SMs for that long slow the step's cluster-scheduled
-GEMMs by ~35 %, so ``host`` is the default on up to 2 GPUs per node.  It costs host DRAM 3x the PCIe
-payload, which 8 ranks cannot afford (4.3 ms/step vs 2.0 for the SM paths): ``auto`` switches to
+GEMMs by ~35 %, so ``host`` is the default for one rank per node.  It costs host DRAM 3x the PCIe
+payload, which several ranks on one socket cannot afford (2 ranks: 3.8 ms/step, 8 ranks: 4.3 vs 2.0
+for the SM paths): ``auto`` switches to
 ``kernel`` there, whose CTAs are small enough to share SMs with the GEMM CTAs.
 """
 from collections import deque
@@ -77,11 +78,12 @@ def default_input_path() -> str:
     """``host`` while the ranks of this node are few enough for host DRAM to carry the staging
     copy (3x the PCIe payload: gather read + staging write + DMA read), else ``kernel`` (1x).
     Measured, 67 MB fp32 batches, ms/step end to end: 1 x B200 host 1.47 | kernel (16 CTAs) 1.53 |
-    kernel (8) 1.69 | tma (2 CTAs) 2.08 | tma (8) 2.85; 4 x B200 host 2.47 | tma 2.03;
+    kernel (8) 1.69 | tma (2 CTAs) 2.08 | tma (8) 2.85; 2 x B200 (one socket) host 3.8;
+    4 x B200 host 2.47 | tma 2.03;
     8 x B200 host 4.3 | tma 2.0 (the box's aggregate H2D rate, ~270 GB/s, is the floor there).
     The LSU kernel's CTAs (256 threads, no shared memory) fit beside the GEMM CTAs on an SM; the
     TMA kernel's 128 KB of staging does not, so each of its CTAs takes an SM from the GEMMs."""
-    return "host" if _local_world() <= 2 else "kernel"
+    return "host" if _local_world() <= 1 else "kernel"
 
 
 def default_gather_threads() -> int:

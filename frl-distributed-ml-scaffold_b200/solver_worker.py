@@ -422,7 +422,7 @@ class SolverWorker:
         self.optimizer.zero_grad()
         if device.type == "cuda":
             import torch.backends.cudnn as cudnn
-            cudnn.benchmark = True
+            cudnn.benchmark = os.environ.get("FRL_B200_CUDNN_BENCHMARK", "1") != "0"
             if precision == Precision.FP32:
                 # parity mode: plain fp32 contractions (TF32 is on by default for convolutions)
                 torch.backends.cuda.matmul.allow_tf32 = False

@@ -201,7 +201,7 @@ class Trace(NamedTuple):
 def train(model: nn.Module, loss_modules: Sequence[nn.Module], loss_weights: Sequence[float],
           loss_names: Sequence[str], datasets: Sequence[Tuple[str, Any]], spec: RunSpec,
           extra_params: Sequence[nn.Parameter] = (), criterion_fn=None,
-          max_steps: Optional[int] = None) -> Trace:
+          max_steps: Optional[int] = None, device: Optional[torch.device] = None) -> Trace:
     """Restatement of SolverWorker.train on one CPU rank (world_size 1).
 
     ``datasets``: ``[(split_name, torch Dataset)]`` in Problem order; the split named
@@ -209,7 +209,16 @@ def train(model: nn.Module, loss_modules: Sequence[nn.Module], loss_weights: Seq
     solver_worker.py:427-442.  Every split is shuffled with a RandomSampler and the planned
     order is drawn once before iterating (solver_worker.py:431, 824-831), which consumes the
     global RNG exactly as the reference does.
+
+    ``device``: run the very same stock-PyTorch loop on that device instead of the CPU (the
+    reference's own GPU path minus DDP: ``model.to(device)`` before the optimizer is built,
+    batches moved per step, solver.py:304-310, solver_worker.py:465-469) — used where CPU-vs-GPU
+    convolution rounding would drown what a test wants to see.
     """
+    if device is not None:
+        model.to(device)
+        for m in loss_modules or ():
+            m.to(device)
     params = list(chain(model.parameters(), extra_params))
     opt = make_optimizer(params, spec.optim)
     model_params = list(model.parameters())
@@ -236,6 +245,9 @@ def train(model: nn.Module, loss_modules: Sequence[nn.Module], loss_weights: Seq
             for data, target, meta in loader:
                 if "index" in meta:
                     order += [int(i) for i in meta["index"]]
+                if device is not None:                     # (:465-469)
+                    data = [t.to(device) for t in data]
+                    target = [tuple(t.to(device) for t in head) for head in target]
                 output = model(data)                       # (:551) data is a List[Tensor]
                 total, sub = criterion_fn(output, target)  # (:567)
                 if torch.isnan(total).any():               # (:569-573)
@@ -246,7 +258,7 @@ def train(model: nn.Module, loss_modules: Sequence[nn.Module], loss_weights: Seq
                     opt.zero_grad()                        # (:585)
                     total.backward()                       # (:586)
                     if first_grads is None:
-                        first_grads = [p.grad.detach().clone().numpy() for p in model_params]
+                        first_grads = [p.grad.detach().cpu().clone().numpy() for p in model_params]
                     if spec.optim.gradient_clip:           # (:588-591) model params only
                         torch.nn.utils.clip_grad_norm_(model_params, spec.optim.gradient_clip)
                     opt.step()                             # (:592)
@@ -261,5 +273,5 @@ def train(model: nn.Module, loss_modules: Sequence[nn.Module], loss_weights: Seq
         if max_steps is not None and steps >= max_steps:
             break
     return Trace(losses=losses, indices=indices, lrs=lrs, first_grads=first_grads,
-                 params=[p.detach().clone().numpy() for p in model_params],
+                 params=[p.detach().cpu().clone().numpy() for p in model_params],
                  loss_names=list(loss_names))

