@@ -1,8 +1,8 @@
-python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_gpu.log
-python bench.py --steps 50 --warmup 10 --profile gpurun_out/trace5.json > gpurun_out/bench_loop.json 2> gpurun_out/bench_loop.err; echo "bench rc=$?"
+python -m pytest tests/test_gpu_resnet.py tests/test_gpu_kernels.py -m gpu -q > gpurun_out/pytest_gpu3.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu3.log
+python bench.py --steps 50 --warmup 10 --algo adam --no-cpu-baseline > gpurun_out/final_bench_n1_adam.json 2> gpurun_out/final_bench_n1_adam.err
 python - <<'PY'
 import json
-for l in open('gpurun_out/bench_loop.json'):
+for l in open('gpurun_out/final_bench_n1_adam.json'):
     if l.startswith('{'):
-        d=json.loads(l); e=d['e2e']; print(round(d['value']), d['ms_per_step'], 'e2e', round(e['value']), e['ms_per_step'], e.get('input_path'), e.get('gpu_launches'), e.get('epoch_losses'))
+        d=json.loads(l); e=d['e2e']; print(round(d['value']), d['ms_per_step'], 'e2e', round(e['value']), e['ms_per_step'], d['roofline']['frac'])
 PY
