@@ -118,13 +118,19 @@ class DeviceBatchLoader:
         self.sampler = self._index_loader.sampler
         self._fields: Dict[str, torch.Tensor] = dataset.pinned_fields
         for name, t in self._fields.items():
-            if not (t.is_pinned() and t.is_contiguous()):
-                raise ValueError(f"field {name!r} must be a contiguous pinned host tensor")
+            if t.is_cuda or not t.is_contiguous():
+                raise ValueError(f"field {name!r} must be a contiguous host tensor")
+        # sources the GPU can read directly (pinned, device-mapped) or only the CPU can (e.g. a
+        # memory-mapped .bin file: served by the host gather pool)
+        all_pinned = all(t.is_pinned() for t in self._fields.values())
         # high priority: the next batch's transfer should start as soon as it is submitted
         self._copy_stream = torch.cuda.Stream(device=device, priority=-1)
         self.path = path or os.environ.get("FRL_B200_INPUT_PATH", "auto")
         if self.path == "auto":
-            self.path = default_input_path()
+            self.path = default_input_path() if all_pinned else "host"
+        if self.path != "host" and not all_pinned:
+            raise ValueError("input path %r needs pinned host tensors; these fields are plain "
+                             "CPU memory (use the host path)" % self.path)
         if self.path not in ("host", "tma", "kernel"):
             raise ValueError(f"unknown input path {self.path!r}")
         self.blocks = int(os.environ.get("FRL_B200_INPUT_BLOCKS", "2" if self.path == "tma" else "16"))

@@ -79,17 +79,16 @@ def _array_dataset_class(ns):
     return ArrayDataset
 
 
-def _pinned_dataset_class(ns):
-    """ArrayDataset whose fields also exist as pinned host tensors + a batched device transform
-    (the B200 input path); the per-sample path stays available and equivalent."""
+def _affine_device_transform(shift: float, scale: float, target_fields):
+    """Batched twin of ``CenteringTransform``: x -> (x - shift) * scale on the device (K5)."""
     import torch
     from . import _native
     from .transform import DeviceBatchTransform
-    Base = _array_dataset_class(ns)
 
     class AffineDeviceTransform(DeviceBatchTransform):
-        def __init__(self, shift: float, scale: float) -> None:
+        def __init__(self) -> None:
             self.shift, self.scale = float(shift), float(scale)
+            self.target_fields = list(target_fields)
             self._coef = {}
 
         def apply(self, raw, split, out_dtype):
@@ -104,16 +103,40 @@ def _pinned_dataset_class(ns):
             # task order is the Problem's: targets are looked up by the tasks' field names
             return [out], [(raw[f],) for f in self.target_fields]
 
+    return AffineDeviceTransform()
+
+
+def _pinned_dataset_class(ns):
+    """ArrayDataset whose fields also exist as pinned host tensors + a batched device transform
+    (the B200 input path); the per-sample path stays available and equivalent."""
+    import torch
+    Base = _array_dataset_class(ns)
+
     class PinnedArrayDataset(Base):
         def __init__(self, split, fields, transform, shift, scale, target_fields) -> None:
             super().__init__(split, fields, transform)
             pin = torch.cuda.is_available()
             self.pinned_fields = {k: (torch.from_numpy(v).pin_memory() if pin else torch.from_numpy(v))
                                   for k, v in fields.items()}
-            self.device_transform = AffineDeviceTransform(shift, scale)
-            self.device_transform.target_fields = list(target_fields)
+            self.device_transform = _affine_device_transform(shift, scale, target_fields)
 
     return PinnedArrayDataset
+
+
+def _indexed_datasets(ns, folder: str, datasets_fields, transform, shift, scale, target_fields):
+    """The same fields written as ``.idx``/``.bin`` files (one sub-folder per split, as the
+    reference lays datasets out) and served from the mapped files."""
+    import os
+    from . import indexed_dataset as idm
+    out = []
+    for split, fields in datasets_fields:
+        sub = os.path.join(folder, split.value)
+        idm.write_fields(sub, fields)
+        names = list(fields)
+        raw = idm.MultifieldIndexedDataset(sub, fields=names, filenames=names)
+        out.append(idm.TransformedIndexedDataset(
+            raw, split, transform, device_transform=_affine_device_transform(shift, scale, target_fields)))
+    return out
 
 
 def _task_classes(ns):
@@ -204,14 +227,17 @@ def _problem_class(ns):
 
         def __init__(self, tasks, trunk_dims: Sequence[int], datasets_fields, save_dir: str,
                      shift: float, scale: float, criterion_kind: str = "parallel",
-                     pinned: bool = False, base_factory=None) -> None:
+                     pinned: bool = False, base_factory=None, indexed_dir: Optional[str] = None) -> None:
             self._tasks = tasks
             self._trunk_dims = list(trunk_dims)
             self._base_factory = base_factory
             self._save_dir = save_dir
             self._criterion_kind = criterion_kind
             self.transform = CenteringTransform(tasks, shift, scale)
-            if pinned:
+            if indexed_dir is not None:
+                self._datasets = _indexed_datasets(ns, indexed_dir, datasets_fields, self.transform,
+                                                   shift, scale, [t._field for t in tasks])
+            elif pinned:
                 ds_cls = _pinned_dataset_class(ns)
                 self._datasets = [ds_cls(split, fields, self.transform, shift, scale,
                                          [t._field for t in tasks])
@@ -269,14 +295,15 @@ def synthetic_fields(n: int, in_dim: int, reg_dim: int, n_classes: int, seed: in
 
 
 def make_toy_problem(ns, save_dir: str, n_train: int = 512, n_test: int = 128,
-                     criterion_kind: str = "parallel", pinned: bool = False):
+                     criterion_kind: str = "parallel", pinned: bool = False,
+                     indexed_dir: Optional[str] = None):
     """Config 1: trunk 64->128->128, reg head 128->4 (w 0.5), cls head 128->10 (w 2)."""
     Reg, Cls = _task_classes(ns)
     tasks = [Reg(128, 4, 0.5), Cls(128, 10, 2.0)]
     fields = [(ns.Split.TRAIN, synthetic_fields(n_train, 64, 4, 10, 0, True)),
               (ns.Split.TEST, synthetic_fields(n_test, 64, 4, 10, 1, True))]
     return _problem_class(ns)(tasks, [64, 128, 128], fields, save_dir, shift=0.5, scale=2.0,
-                              criterion_kind=criterion_kind, pinned=pinned)
+                              criterion_kind=criterion_kind, pinned=pinned, indexed_dir=indexed_dir)
 
 
 def synthetic_fields_fast(n: int, in_dim: int, reg_dim: int, n_classes: int, seed: int

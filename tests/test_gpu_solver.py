@@ -222,3 +222,27 @@ def test_device_batch_loader_path_matches_reference_solver(ns, golden_dir, monke
         assert set(got) == set(want) and len(want) >= 2
         for k in want:
             assert got[k] == pytest.approx(want[k], rel=1e-5, abs=1e-7), (split, k)
+
+
+def test_indexed_files_feed_the_loop_through_the_host_pool(ns, golden_dir, monkeypatch, tmp_path):
+    """the toy Problem's datasets written as .idx/.bin files (this repo's writer,
+    byte-identical to the reference's) and served from the memory-mapped files — the host gather
+    pool copies each minibatch's frames from the page cache into pinned staging, one DMA per field,
+    transform on the device.  Same samples in the same order => the golden per-step losses."""
+    import frl_b200.synthetic as syn
+    g = np.load(os.path.join(golden_dir, "toy_sgd.npz"))
+    orig = syn.make_toy_problem
+    monkeypatch.setattr(syn, "make_toy_problem",
+                        lambda ns_, save_dir, **kw: orig(ns_, save_dir, indexed_dir=str(tmp_path), **kw))
+    summaries, worker, problem, _ = _solve_and_capture(ns, CONFIGS["toy_sgd"])
+    assert sorted(os.listdir(tmp_path / "training")) == ["x.bin", "x.idx", "y_cls.bin", "y_cls.idx",
+                                                          "y_reg.bin", "y_reg.idx"]
+    assert not any(t.is_pinned() for t in problem.datasets[0].pinned_fields.values())
+    rows = np.concatenate([r for _, _, r in worker.loss_history])
+    np.testing.assert_allclose(rows, g["rows"], rtol=1e-5, atol=1e-6)
+    # and the per-sample protocol over the same files equals the in-memory dataset's
+    plain = orig(ns, "/tmp/unused")
+    for i in (0, 17, 511):
+        a, b = problem.datasets[0][i], plain.datasets[0][i]
+        assert torch.equal(a[0][0], b[0][0]) and torch.equal(a[1][0][0], b[1][0][0])
+        assert torch.equal(a[1][1][0], b[1][1][0]) and int(a[2]["index"]) == int(b[2]["index"]) == i
