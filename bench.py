@@ -447,6 +447,7 @@ def main_b200(args, rank, local_rank, world):
                "d2h_bytes_per_step": 4 * (1 + n_tasks) + 4 * n_metrics * B,
                "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "input_path": loader.path,
                "input_threads": loader.threads, "input_blocks": loader.blocks,
+               "input_wire": {k: str(v).replace("torch.", "") for k, v in loader._wire_dtype.items()},
                "gpu_launches": e2e_launches,
                "epoch_losses": {k: float(v) for k, v in ep_losses.items()},
                "how": "SolverWorker._pass_one_epoch (the loop Solver.solve runs per epoch) over the "

@@ -64,6 +64,7 @@ SIGNATURES = {
     "frl_gather_pool_destroy": (None, [_vp]),
     "frl_gather_pool_threads": (_i, [_vp]),
     "frl_gather_pool_submit": (_i64, [_vp, _vp, _i64, _vp, _vp, _i64, _i64]),
+    "frl_gather_pool_submit_f32_to_bf16": (_i64, [_vp, _vp, _i64, _vp, _vp, _i64, _i64]),
     "frl_gather_pool_wait": (_i, [_vp, _i64]),
     "frl_nvls_sgd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d, _vp, _i, _i, _i, _vp]),
     "frl_nvls_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d,
@@ -312,6 +313,20 @@ class HostGatherPool:
                                              _ptr(dst_host), idx_host.numel(), _row_bytes(src)))
         if t < 1:
             _check(t if t != 0 else -1, "frl_gather_pool_submit")
+        return t
+
+    def submit_f32_to_bf16(self, src, idx_host, dst_host) -> int:
+        """Queue dst_host[i] = bfloat16(src[idx_host[i]]) (round to nearest even) for fp32 ``src``."""
+        assert src.dtype == torch.float32 and dst_host.dtype == torch.bfloat16
+        assert src.is_contiguous() and dst_host.is_contiguous()
+        assert not src.is_cuda and not dst_host.is_cuda and not idx_host.is_cuda
+        assert idx_host.dtype == torch.int64 and idx_host.is_contiguous()
+        assert dst_host.shape[0] >= idx_host.numel() and dst_host.shape[1:] == src.shape[1:]
+        row_elems = src[0].numel() if src.shape[0] else 0
+        t = int(lib().frl_gather_pool_submit_f32_to_bf16(self._h, _ptr(src), src.shape[0], _ptr(idx_host),
+                                                         _ptr(dst_host), idx_host.numel(), row_elems))
+        if t < 1:
+            _check(t if t != 0 else -1, "frl_gather_pool_submit_f32_to_bf16")
         return t
 
     def wait(self, ticket: int) -> None:

@@ -134,10 +134,19 @@ class DeviceBatchLoader:
         if self.path not in ("host", "tma", "kernel"):
             raise ValueError(f"unknown input path {self.path!r}")
         self.blocks = int(os.environ.get("FRL_B200_INPUT_BLOCKS", "2" if self.path == "tma" else "16"))
+        # wire dtype per field: fp32 fields the transform declares bf16-tolerant travel as bf16 when
+        # the run computes in bf16 and FRL_B200_INPUT_WIRE=bf16 (host path: the gather threads convert)
+        self.wire = os.environ.get("FRL_B200_INPUT_WIRE", "native")
+        tolerant = set(getattr(dataset.device_transform, "bf16_wire_fields", ()) or ())
+        self._wire_dtype: Dict[str, torch.dtype] = {}
+        for name, t in self._fields.items():
+            cvt = (self.wire == "bf16" and self.path == "host" and out_dtype == torch.bfloat16
+                   and t.dtype == torch.float32 and name in tolerant)
+            self._wire_dtype[name] = torch.bfloat16 if cvt else t.dtype
         self._slots = []
         for _ in range(self.depth):
-            slot = {name: torch.empty((batch_size,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
-                    for name, t in self._fields.items()}
+            slot = {name: torch.empty((batch_size,) + tuple(t.shape[1:]), dtype=self._wire_dtype[name],
+                                      device=device) for name, t in self._fields.items()}
             slot["__idx_host"] = torch.empty(batch_size, dtype=torch.int64, pin_memory=True)
             slot["__idx_dev"] = torch.empty(batch_size, dtype=torch.int64, device=device)
             self._slots.append(slot)
@@ -149,14 +158,16 @@ class DeviceBatchLoader:
             self._pool = _native.HostGatherPool(default_gather_threads())
             self.threads = self._pool.n_threads
             self._n_stage = self.depth + 1
-            self._stage = [{name: torch.empty((batch_size,) + tuple(t.shape[1:]), dtype=t.dtype,
-                                              pin_memory=True) for name, t in self._fields.items()}
+            self._stage = [{name: torch.empty((batch_size,) + tuple(t.shape[1:]),
+                                              dtype=self._wire_dtype[name], pin_memory=True)
+                            for name, t in self._fields.items()}
                            for _ in range(self._n_stage)]
             self._stage_idx = [torch.empty(batch_size, dtype=torch.int64, pin_memory=True)
                                for _ in range(self._n_stage)]
             self._dma_done = [torch.cuda.Event() for _ in range(self._n_stage)]
-        self.h2d_bytes_per_batch = sum(t[0].numel() * t.element_size() for t in self._fields.values()
-                                       ) * batch_size + 8 * batch_size
+        self.h2d_bytes_per_batch = sum(
+            t[0].numel() * torch.empty(0, dtype=self._wire_dtype[name]).element_size()
+            for name, t in self._fields.items()) * batch_size + 8 * batch_size
 
     def __len__(self) -> int:
         return len(self._index_loader)
@@ -216,7 +227,10 @@ class DeviceBatchLoader:
         self._stage_idx[st][:n].copy_(idx)
         ticket = 0
         for name, src in self._fields.items():
-            ticket = self._pool.submit(src, idx, self._stage[st][name])
+            if self._wire_dtype[name] != src.dtype:
+                ticket = self._pool.submit_f32_to_bf16(src, idx, self._stage[st][name])
+            else:
+                ticket = self._pool.submit(src, idx, self._stage[st][name])
         return st, n, ticket
 
     def _issue_dma(self, k: int, st: int, n: int, ticket: int) -> int:

@@ -86,6 +86,8 @@ def _affine_device_transform(shift: float, scale: float, target_fields):
     from .transform import DeviceBatchTransform
 
     class AffineDeviceTransform(DeviceBatchTransform):
+        bf16_wire_fields = ("x",)
+
         def __init__(self) -> None:
             self.shift, self.scale = float(shift), float(scale)
             self.target_fields = list(target_fields)

@@ -45,6 +45,11 @@ class DeviceBatchTransform(ABC):
     ``out_dtype``).  ``meta`` returns the collated meta dict (tensors on any device / lists).
     """
 
+    #: fp32 fields ``apply`` is happy to receive already rounded to bfloat16 when ``out_dtype`` is
+    #: bfloat16 (typically the model inputs).  The host input path may then ship them over PCIe in
+    #: bf16 (``FRL_B200_INPUT_WIRE=bf16``); targets and anything exact must not be listed.
+    bf16_wire_fields: Sequence[str] = ()
+
     @abstractmethod
     def apply(self, raw: Dict[str, Tensor], split: Split, out_dtype
               ) -> Tuple[List[Tensor], List[Tuple[Tensor, ...]]]:

@@ -248,6 +248,12 @@ int frl_gather_pool_threads(const frl_gather_pool* pool);
 int64_t frl_gather_pool_submit(frl_gather_pool* pool, const void* src_host, int64_t src_rows,
                                const int64_t* idx_host, void* dst_host, int64_t n_rows,
                                int64_t row_bytes);
+/* Same gather with the PCIe hop in bf16: src rows are fp32 [row_elems], dst rows bf16 [row_elems],
+ * converted round-to-nearest-even (NaN -> quiet NaN), bit-identical to the device cast, while the
+ * worker threads touch the bytes anyway.  Halves the H2D payload of a bf16-compute run. */
+int64_t frl_gather_pool_submit_f32_to_bf16(frl_gather_pool* pool, const void* src_host,
+                                           int64_t src_rows, const int64_t* idx_host, void* dst_host,
+                                           int64_t n_rows, int64_t row_elems);
 int frl_gather_pool_wait(frl_gather_pool* pool, int64_t ticket);
 
 #ifdef __cplusplus

@@ -246,3 +246,37 @@ def test_indexed_files_feed_the_loop_through_the_host_pool(ns, golden_dir, monke
         a, b = problem.datasets[0][i], plain.datasets[0][i]
         assert torch.equal(a[0][0], b[0][0]) and torch.equal(a[1][0][0], b[1][0][0])
         assert torch.equal(a[1][1][0], b[1][1][0]) and int(a[2]["index"]) == int(b[2]["index"]) == i
+
+
+def test_bf16_wire_format_of_the_host_input_path(ns, golden_dir, monkeypatch):
+    """FRL_B200_INPUT_WIRE=bf16: in a bf16-compute run the host gather threads round the model
+    inputs to bf16 (bit-identical to the device cast) so PCIe carries half the bytes; targets stay
+    exact.  The run stays within the bf16 bound of the fp32 reference, and the wire dtype is
+    really used."""
+    import frl_b200.synthetic as syn
+    from frl_b200 import device_loader
+    g = np.load(os.path.join(golden_dir, "toy_sgd.npz"))
+    orig = syn.make_toy_problem
+    monkeypatch.setattr(syn, "make_toy_problem",
+                        lambda ns_, save_dir, **kw: orig(ns_, save_dir, pinned=True, **kw))
+    monkeypatch.setenv("FRL_B200_INPUT_PATH", "host")
+    monkeypatch.setenv("FRL_B200_INPUT_WIRE", "bf16")
+    seen = []
+    real_init = device_loader.DeviceBatchLoader.__init__
+
+    def spy(self, *a, **kw):
+        real_init(self, *a, **kw)
+        seen.append(dict(self._wire_dtype))
+
+    monkeypatch.setattr(device_loader.DeviceBatchLoader, "__init__", spy)
+    _, worker, problem, _ = _solve_and_capture(ns, CONFIGS["toy_sgd"], precision=Precision.BF16)
+    assert seen and all(w["x"] == torch.bfloat16 and w["y_reg"] == torch.float32
+                        and w["y_cls"] == torch.int64 for w in seen)
+    rows = np.concatenate([r for _, _, r in worker.loss_history])
+    np.testing.assert_allclose(rows, g["rows"], rtol=1e-2, atol=1e-3)
+    # fp32 runs ignore the switch: parity mode never rounds its inputs
+    seen.clear()
+    _, worker, _, _ = _solve_and_capture(ns, CONFIGS["toy_sgd"])
+    assert seen and all(w["x"] == torch.float32 for w in seen)
+    rows = np.concatenate([r for _, _, r in worker.loss_history])
+    np.testing.assert_allclose(rows, g["rows"], rtol=1e-5, atol=1e-6)

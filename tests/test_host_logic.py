@@ -282,3 +282,35 @@ def test_planned_order_for_the_null_accessor_only_draws_the_seed():
     assert _planned_order(sampler, object()) == full           # a real cache accessor gets the order
     seq = tud.SequentialSampler(range(5))
     assert _planned_order(seq, NullAccessor()) == [0, 1, 2, 3, 4]
+
+
+def test_host_pool_bf16_wire_conversion_is_bit_identical_to_torch():
+    from frl_b200 import _native
+    pool = _native.HostGatherPool(2)
+    rs = np.random.RandomState(0)
+    vals = (rs.randn(300, 1037) * 10.0 ** rs.randint(-30, 30, size=(300, 1))).astype(np.float32)
+    src = torch.from_numpy(vals)
+    # exact ties, subnormals, infinities, NaNs, the largest finite value, signed zeros
+    special = torch.tensor([1.00390625, 1.01171875, -1.00390625, 3.3895313892515355e38, 1e-40, -1e-45,
+                            float("inf"), float("-inf"), float("nan"), 0.0, -0.0, 65504.0, 1.0 + 2 ** -8,
+                            1.0 + 2 ** -8 + 2 ** -20], dtype=torch.float32)
+    src[0, :len(special)] = special
+    nan_payload = torch.tensor([0x7f800001, 0xffc12345], dtype=torch.int64).to(torch.int32).view(torch.float32)
+    src[1, :2] = nan_payload
+    idx = torch.cat([torch.tensor([0, 1]), torch.randint(0, 300, (70,))])
+    out = torch.zeros(len(idx), 1037, dtype=torch.bfloat16)
+    pool.wait(pool.submit_f32_to_bf16(src, idx, out))
+    want = src[idx].to(torch.bfloat16)
+    got_bits, want_bits = out.view(torch.int16), want.view(torch.int16)
+    nan = torch.isnan(want)
+    assert torch.equal(got_bits[~nan], want_bits[~nan])
+    assert torch.isnan(out[nan]).all() and nan.sum() >= 3
+    # unaligned destination rows (odd row length) and a row shorter than one vector
+    small = torch.randn(50, 5)
+    out2 = torch.zeros(9, 5, dtype=torch.bfloat16)
+    i2 = torch.randint(0, 50, (9,))
+    pool.wait(pool.submit_f32_to_bf16(small, i2, out2))
+    assert torch.equal(out2, small[i2].to(torch.bfloat16))
+    with pytest.raises(_native.NativeLibraryError):
+        pool.submit_f32_to_bf16(small, torch.tensor([50]), out2)
+    pool.close()
