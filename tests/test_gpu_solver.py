@@ -280,3 +280,28 @@ def test_bf16_wire_format_of_the_host_input_path(ns, golden_dir, monkeypatch):
     assert seen and all(w["x"] == torch.float32 for w in seen)
     rows = np.concatenate([r for _, _, r in worker.loss_history])
     np.testing.assert_allclose(rows, g["rows"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("path", ["host", "kernel", "tma"])
+def test_batched_input_path_with_a_ragged_last_batch(ns, monkeypatch, path):
+    """512 and 128 samples at batch 48: the last minibatch of every split is short.  The batched
+    path must serve exactly what the per-sample DataLoader path serves (same solver underneath):
+    identical per-step losses, sample counts and amortised metrics."""
+    import frl_b200.synthetic as syn
+    cfg = CONFIGS["toy_sgd"]
+    plain, w_plain, _, _ = _solve_and_capture(ns, cfg, batchSize=48, nEpochs=1, metricAmortizationSchedule=3)
+    orig = syn.make_toy_problem
+    monkeypatch.setattr(syn, "make_toy_problem",
+                        lambda ns_, save_dir, **kw: orig(ns_, save_dir, pinned=True, **kw))
+    monkeypatch.setenv("FRL_B200_INPUT_PATH", path)
+    fast, w_fast, problem, _ = _solve_and_capture(ns, cfg, batchSize=48, nEpochs=1, metricAmortizationSchedule=3)
+    assert problem.datasets[0].served == []
+    a = np.concatenate([r for _, _, r in w_plain.loss_history])
+    b = np.concatenate([r for _, _, r in w_fast.loss_history])
+    assert a.shape == b.shape == (11 + 3, 3)
+    np.testing.assert_allclose(b, a, rtol=1e-6, atol=1e-7)
+    for split in (ns.Split.TRAIN, ns.Split.TEST):
+        pa, pb = plain[-1].performance[split], fast[-1].performance[split]
+        assert pa.nSamples == pb.nSamples
+        for k in pa.metrics:
+            assert pb.metrics[k] == pytest.approx(pa.metrics[k], rel=1e-6, abs=1e-8)
