@@ -81,6 +81,11 @@ def time_cpu_reference(algo, batch, steps, warmup):
     import frl_b200  # noqa: F401  (only the synthetic Problem definition)
     from frl_b200 import synthetic
     from oracle import ref_loop
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 by default)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except AttributeError:
+        torch.set_num_threads(os.cpu_count() or 1)
     ns = synthetic.api_namespace("frl_b200")
     torch.manual_seed(0)
     problem = build_problem(ns, "/tmp/frl_b200_bench_cpu")
@@ -107,8 +112,8 @@ def time_cpu_reference(algo, batch, steps, warmup):
         if i >= warmup:
             times.append(dt)
     total = sum(times)
-    return {"value": batch * steps / total, "unit": "samples/s", "cores": os.cpu_count(),
-            "torch_threads": torch.get_num_threads(), "kind": "port",
+    return {"value": batch * steps / total, "unit": "samples/s", "cores": torch.get_num_threads(),
+            "host_cpus": os.cpu_count(), "kind": "port",
             "sample": "%d timed steps (+%d warm-up) of the same 2-task MLP at batch %d, fp32, "
                       "oracle/ref_loop.reference_minibatch (stock torch CPU ops + torch.optim)" % (
                           steps, warmup, batch),
