@@ -151,3 +151,157 @@ def test_bf16_round_matches_torch():
     x = np.random.RandomState(1).randn(4097).astype(np.float32) * 3
     want = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
     assert np.array_equal(optim_np.bf16_round(x), want)
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY §8 a16 — SamplerState (retained minibatches -> per-sample metrics, random picks, worst-k)
+# against the live reference class on identical inputs
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.reference
+@pytest.mark.parametrize("metric_name,ordering", [("err_MSE", "DESC"), ("score", "ASC"), ("score", "DESC")])
+def test_sampler_state_matches_live_reference(metric_name, ordering):
+    import random
+    from typing import NamedTuple
+    from oracle.ref_shim import import_reference
+    import_reference()
+    import frldistml.scaffold.solver_worker as ref_sw
+    from frldistml.scaffold.problem import Ordering as RefOrdering
+    import frl_b200  # noqa: F401
+    import frl_b200.solver_worker as my_sw
+    from frl_b200.problem import Ordering as MyOrdering
+
+    class Meta(NamedTuple):
+        index: object = None
+
+    def make_problem(Ordering):
+        class P:
+            def refine_batch_meta(self, meta):
+                return Meta(**meta)
+
+            def compute_batch_metrics(self, meta, target, output, device):
+                err = ((output[0] - target[0][0]) ** 2).mean(1).numpy()
+                score = (output[1][:, 0] - target[1][0].float()).numpy()      # signed, tie-free
+                return {"err_MSE": err, "score": score}
+
+            def get_rankable_metric(self):
+                return metric_name, Ordering[ordering]
+        return P()
+
+    g = torch.Generator().manual_seed(11)
+    sizes = [16, 16, 16, 16, 9]                       # ragged last minibatch
+    batches, start = [], 0
+    for n in sizes:
+        batches.append(dict(
+            meta={"index": torch.arange(start, start + n)},
+            data=[torch.randn(n, 5, generator=g)],
+            outputs=[torch.randn(n, 4, generator=g), torch.randn(n, 3, generator=g)],
+            targets=[(torch.randn(n, 4, generator=g),), (torch.randint(0, 3, (n,), generator=g),)]))
+        start += n
+    total = start
+
+    class FakeLoader:
+        sampler = list(range(total))
+
+    dev = torch.device("cpu")
+    random.seed(5)
+    ref = ref_sw.SamplerState(make_problem(RefOrdering), FakeLoader, list(range(total)), dev, 6)
+    random.seed(5)
+    mine = my_sw.SamplerState(make_problem(MyOrdering), total, total, dev, 6)
+    for s in (ref, mine):
+        for k, b in enumerate(batches):
+            if k % 2 == 0:                            # amortisation: fold every second minibatch
+                s.compute_metrics()
+            s.append_sample(b["meta"], b["data"], outputs=b["outputs"], targets=b["targets"])
+        s.compute_metrics()
+    mine.finish()
+
+    assert mine.n_samples == ref.n_samples == total
+    for k in ("err_MSE", "score"):
+        np.testing.assert_array_equal(np.asarray(mine.data_metric[k]), np.asarray(ref.data_metric[k]))
+
+    def ids(samples):
+        return [int(s.meta["index"]) for s in samples]
+
+    assert ids(mine.random_samples) == ids(ref.random_samples) and len(ids(ref.random_samples)) == 6
+    assert sorted(ids(mine.worst_samples)) == sorted(ids(ref.worst_samples))
+    assert len(ref.worst_samples) == 6
+    by_id = {int(s.meta["index"]): s for s in ref.worst_samples + ref.random_samples}
+    for s in mine.worst_samples + mine.random_samples:
+        r = by_id[int(s.meta["index"])]
+        assert all(torch.equal(a, b) for a, b in zip(s.data, r.data))
+        assert all(torch.equal(a, b) for a, b in zip(s.output, r.output))
+        assert all(torch.equal(a[0], b[0]) for a, b in zip(s.target, r.target))
+        assert {k: float(v) for k, v in s.metric.items()} == {k: float(v) for k, v in r.metric.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY §8 a8-a11 — the criterion classes' own composition (what runs for arbitrary user losses,
+# and what the fused kernels are checked against on the GPU) against the live reference classes
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.reference
+@pytest.mark.parametrize("kind", ["parallel", "uncertainty", "gradnorm", "masked"])
+def test_criterion_classes_match_live_reference(kind):
+    from oracle.ref_shim import import_reference
+    import_reference()
+    import frldistml.scaffold.criteria as ref_c
+    import frldistml.scaffold.model as ref_m
+    import frldistml.scaffold.types as ref_t
+    import frl_b200  # noqa: F401
+    import frl_b200.criteria as my_c
+    import frl_b200.model as my_m
+    import frl_b200.types as my_t
+
+    def build(c, m, t):
+        torch.manual_seed(3)
+        trunk = torch.nn.Sequential(m.ListSelect(sel_index=0, num_elements=1), torch.nn.Linear(6, 8),
+                                    torch.nn.ReLU(), torch.nn.Linear(8, 8), torch.nn.ReLU())
+        model = m.MultiTaskModel(trunk, [torch.nn.Linear(8, 3), torch.nn.Linear(8, 5)])
+        mods = [torch.nn.MSELoss(), torch.nn.CrossEntropyLoss()]
+        names, weights = ["reg", "cls"], [0.5, 2.0]
+        if kind == "parallel":
+            crit = c.ParallelCriterion(mods, weights, names)
+        elif kind == "uncertainty":
+            crit = c.UncertaintyWeightedCriterion(
+                mods, [t.LossType.MSE, t.LossType.CrossEntropy], names, weights)
+        elif kind == "gradnorm":
+            crit = c.GradNormWeightedCriterion(mods, names, alpha=1.5, base_weights=weights)
+        else:
+            crit = c.ParallelCriterion([c.MaskedLoss(torch.nn.MSELoss()), torch.nn.CrossEntropyLoss()],
+                                       weights, names)
+        return model, crit
+
+    g = torch.Generator().manual_seed(4)
+    steps = []
+    for k in range(4):
+        x = torch.randn(12, 6, generator=g)
+        y_reg, y_cls = torch.randn(12, 3, generator=g), torch.randint(0, 5, (12,), generator=g)
+        mask = (torch.rand(12, 3, generator=g) > 0.4) if k != 2 else torch.zeros(12, 3, dtype=torch.bool)
+        steps.append((x, y_reg, y_cls, mask))
+
+    def run(c, m, t):
+        model, crit = build(c, m, t)
+        params = list(model.parameters()) + list(crit.parameters())
+        opt = torch.optim.SGD(params, lr=0.05, momentum=0.9)
+        trace = []
+        for x, y_reg, y_cls, mask in steps:
+            out = model([x])
+            if kind == "gradnorm":
+                crit.set_shared_params(model.final_shared_params(out))
+            tgt = [(y_reg, mask) if kind == "masked" else (y_reg,), (y_cls,)]
+            total, sub = crit(out, tgt)
+            opt.zero_grad()
+            total.backward()
+            trace.append((total.detach().clone(), {k: v.detach().clone() for k, v in sub.items()},
+                          [p.grad.detach().clone() for p in params]))
+            opt.step()
+        return trace, [p.detach().clone() for p in params]
+
+    ref_trace, ref_params = run(ref_c, ref_m, ref_t)
+    my_trace, my_params = run(my_c, my_m, my_t)
+    for (rt, rs, rg), (mt, ms, mg) in zip(ref_trace, my_trace):
+        assert torch.equal(mt, rt)
+        assert list(ms) == list(rs) and all(torch.equal(ms[k], rs[k]) for k in rs)
+        assert len(mg) == len(rg) and all(torch.equal(a, b) for a, b in zip(mg, rg))
+    assert all(torch.equal(a, b) for a, b in zip(my_params, ref_params))
