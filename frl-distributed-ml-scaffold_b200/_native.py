@@ -58,6 +58,7 @@ SIGNATURES = {
     "frl_cast_scale": (_i, [_vp, _i, _vp, _i, _i64, _f, _vp]),
     "frl_colsum_scratch_bytes": (_i64, [_i64, _i64]),
     "frl_colsum": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i, _vp, _vp]),
+    "frl_drelu_colsum": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _i, _i, _vp, _vp]),
     "frl_gather_rows": (_i, [_vp, _i64, _vp, _vp, _i64, _i64, _i, _vp]),
     "frl_gather_rows_tma": (_i, [_vp, _i64, _vp, _vp, _i64, _i64, _i, _vp]),
     "frl_gather_pool_create": (_vp, [_i]),
@@ -232,6 +233,21 @@ def colsum(x, out, accumulate: bool = False) -> None:
     _check(lib().frl_colsum(_ptr(x), dtype_code(x.dtype), rows, cols, _ptr(out),
                             dtype_code(out.dtype), int(accumulate), _ptr(buf), _stream()),
            "frl_colsum")
+
+
+def drelu_colsum(dy, act, dz, out, accumulate: bool = False) -> None:
+    """dz = where(act > 0, dy, 0); out[c] (+)= sum_r dz[r, c] — one pass (contiguous 2-D inputs)."""
+    rows, cols = dy.shape
+    assert act.shape == dy.shape == dz.shape and act.dtype == dy.dtype == dz.dtype
+    assert dy.is_contiguous() and act.is_contiguous() and dz.is_contiguous()
+    key = (dy.device.index, cols)
+    need = int(lib().frl_colsum_scratch_bytes(rows, cols))
+    buf = _colsum_scratch.get(key)
+    if buf is None or buf.numel() * 4 < need:
+        buf = _colsum_scratch[key] = torch.zeros((need + 3) // 4, dtype=torch.int32, device=dy.device)
+    _check(lib().frl_drelu_colsum(_ptr(dy), _ptr(act), _ptr(dz), dtype_code(dy.dtype), rows, cols,
+                                  _ptr(out), dtype_code(out.dtype), int(accumulate), _ptr(buf), _stream()),
+           "frl_drelu_colsum")
 
 
 # ---- K7 -------------------------------------------------------------------------------------

@@ -14,8 +14,20 @@ this autograd Function while the model is wrapped:
 so the bucket NCCL reduces is complete the moment the layer's backward returns: no flatten
 copy, no separate bias-reduction pass through a generic reduce kernel.  Outside a pipeline
 step (``autograd.grad`` calls of GradNorm / debugGrad) the Function returns ordinary gradients.
+
+``FRL_B200_FUSE_RELU=1``: a ``nn.Linear`` directly followed by a ``nn.ReLU`` inside a
+``nn.Sequential`` (each module used exactly once, no hooks) runs as one unit:
+
+  forward   y = relu(x W^T + b)                one cuBLASLt GEMM with the bias+ReLU epilogue
+                                               (``torch._addmm_activation``); the ReLU module
+                                               becomes a pass-through
+  backward  dZ = (y > 0) * dY, db = colsum(dZ) ONE pass (``frl_drelu_colsum``, K6b) instead of
+                                               threshold_backward + a reduction
+            dX = dZ W, dW = dZ^T X             as above
 """
+import os
 import types
+from collections import Counter
 from typing import List, Optional
 
 import torch
@@ -66,9 +78,54 @@ class _ArenaLinearFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class _ArenaLinearReluFn(torch.autograd.Function):
+    """relu(linear(x)) as one unit; see the module docstring."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, site):
+        ctx.site = site
+        x2 = x.reshape(-1, x.shape[-1])
+        y2 = torch._addmm_activation(bias, x2, weight.t(), use_gelu=False)
+        y = y2.view(*x.shape[:-1], weight.shape[0])
+        ctx.save_for_backward(x, weight, y)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        site = ctx.site
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        y2 = y.reshape(-1, y.shape[-1])
+        x2 = x.reshape(-1, x.shape[-1])
+        pipe = site.pipeline
+        if pipe is not None and pipe.step_open and dy2.is_cuda:
+            first = site.touched_step != pipe.step_id
+            site.touched_step = pipe.step_id
+            dz = torch.empty_like(dy2)
+            KERNELS.drelu_colsum(dy2, y2, dz, pipe.arena.grad_view(site.bslot), accumulate=not first)
+            # dX before any slot is marked ready (the bucket's update overwrites W)
+            dx = dz.matmul(weight).view_as(x) if ctx.needs_input_grad[0] else None
+            gw = pipe.arena.grad_view(site.wslot)
+            if first:
+                torch.mm(dz.t(), x2, out=gw)
+            else:
+                gw.addmm_(dz.t(), x2)
+            pipe.mark_ready(site.wslot)
+            pipe.mark_ready(site.bslot)
+            return dx, None, None, None
+        dz = dy2 * (y2 > 0).to(dy2.dtype)
+        dx = dz.matmul(weight).view_as(x) if ctx.needs_input_grad[0] else None
+        dw = dz.t().mm(x2) if ctx.needs_input_grad[1] else None
+        db = dz.sum(0) if ctx.needs_input_grad[2] else None
+        return dx, dw, db, None
+
+
 class LinearSite:
     """Per-module bookkeeping: arena slots of weight/bias and the owning pipeline."""
-    __slots__ = ("module", "wslot", "bslot", "pipeline", "touched_step")
+    __slots__ = ("module", "wslot", "bslot", "pipeline", "touched_step", "relu")
 
     def __init__(self, module, wslot, bslot, pipeline):
         self.module = module
@@ -76,10 +133,47 @@ class LinearSite:
         self.bslot = bslot
         self.pipeline = pipeline
         self.touched_step = -1
+        self.relu = None              # the nn.ReLU this layer absorbed (FRL_B200_FUSE_RELU)
 
 
 def _forward(self, x):
     return _ArenaLinearFn.apply(x, self.weight, self.bias, self._frl_site)
+
+
+def _forward_relu(self, x):
+    return _ArenaLinearReluFn.apply(x, self.weight, self.bias, self._frl_site)
+
+
+def _identity(self, x):
+    return x
+
+
+def _has_hooks(mod: nn.Module) -> bool:
+    return bool(mod._forward_hooks or mod._forward_pre_hooks or mod._backward_hooks
+                or getattr(mod, "_backward_pre_hooks", None))
+
+
+def _fuse_relu_pairs(model: nn.Module, sites: List[LinearSite]) -> int:
+    """Mark Linear -> ReLU neighbours of nn.Sequential containers as fused units."""
+    uses = Counter(id(child) for mod in model.modules() for child in mod._modules.values()
+                   if child is not None)
+    by_module = {id(s.module): s for s in sites}
+    fused = 0
+    for seq in model.modules():
+        if type(seq) is not nn.Sequential:
+            continue
+        kids = list(seq._modules.values())
+        for lin, act in zip(kids, kids[1:]):
+            site = by_module.get(id(lin))
+            if site is None or site.bslot is None or type(act) is not nn.ReLU or site.relu is not None:
+                continue
+            if uses[id(lin)] != 1 or uses[id(act)] != 1 or _has_hooks(lin) or _has_hooks(act):
+                continue
+            if "forward" in act.__dict__:
+                continue
+            site.relu = act
+            fused += 1
+    return fused
 
 
 def patch_linears(model: nn.Module, pipeline) -> List[LinearSite]:
@@ -96,9 +190,10 @@ def patch_linears(model: nn.Module, pipeline) -> List[LinearSite]:
         if mod.bias is not None and bslot is None:
             continue                     # frozen bias: leave the module alone
         site = LinearSite(mod, wslot, bslot, pipeline)
-        mod._frl_site = site
-        mod.forward = types.MethodType(_forward, mod)
         sites.append(site)
+    if os.environ.get("FRL_B200_FUSE_RELU", "0") != "0":
+        _fuse_relu_pairs(model, sites)
+    repatch_linears(sites)
     return sites
 
 
@@ -106,9 +201,15 @@ def unpatch_linears(sites: List[LinearSite]) -> None:
     for site in sites:
         site.module.__dict__.pop("forward", None)
         site.module.__dict__.pop("_frl_site", None)
+        if site.relu is not None:
+            site.relu.__dict__.pop("forward", None)
 
 
 def repatch_linears(sites: List[LinearSite]) -> None:
     for site in sites:
         site.module._frl_site = site
-        site.module.forward = types.MethodType(_forward, site.module)
+        if site.relu is not None:
+            site.module.forward = types.MethodType(_forward_relu, site.module)
+            site.relu.forward = types.MethodType(_identity, site.relu)
+        else:
+            site.module.forward = types.MethodType(_forward, site.module)

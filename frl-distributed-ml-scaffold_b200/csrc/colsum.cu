@@ -38,10 +38,24 @@ template <typename T> __device__ __forceinline__ void st1(T* p, float v);
 template <> __device__ __forceinline__ void st1<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void st1<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-// partial layout: [tile][split][kSCols] floats, after the per-tile tickets
-template <typename XT, typename OT, bool VEC>
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+    st_stream(reinterpret_cast<f32x4*>(p), f32x4{v[0], v[1], v[2], v[3]});
+    st_stream(reinterpret_cast<f32x4*>(p) + 1, f32x4{v[4], v[5], v[6], v[7]});
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+    st_stream(reinterpret_cast<bf16x8*>(p), bf16x8{pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                   pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])});
+}
+
+// partial layout: [tile][split][kSCols] floats, after the per-tile tickets.
+// MASK (K6b): x is dY of a ReLU layer, `act` its forward output; dZ = act > 0 ? dY : 0 is written
+// to `dz` on the way and the column sums are those of dZ — ReLU's backward and the bias-gradient
+// reduction in the one pass over dY that the reduction needs anyway.
+template <typename XT, typename OT, bool VEC, bool MASK>
 __global__ void __launch_bounds__(kSThreads)
-colsum_kernel(const XT* __restrict__ x, int64_t rows, int64_t cols, OT* __restrict__ out,
+colsum_kernel(const XT* __restrict__ x, const XT* __restrict__ act, XT* __restrict__ dz, int64_t rows,
+              int64_t cols, OT* __restrict__ out,
               int accumulate, unsigned int* __restrict__ tickets, float* __restrict__ partial) {
     __shared__ float sm[kSWarps][kSCols];
     __shared__ bool is_last;
@@ -57,6 +71,13 @@ colsum_kernel(const XT* __restrict__ x, int64_t rows, int64_t cols, OT* __restri
                  r += static_cast<int64_t>(nsplit) * kSWarps) {
                 float v[8];
                 load8<XT>(x + r * cols + c0, v);
+                if (MASK) {
+                    float a[8];
+                    load8<XT>(act + r * cols + c0, a);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = a[k] > 0.f ? v[k] : 0.f;
+                    store8<XT>(dz + r * cols + c0, v);
+                }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc[k] += v[k];
             }
@@ -66,7 +87,14 @@ colsum_kernel(const XT* __restrict__ x, int64_t rows, int64_t cols, OT* __restri
              r += static_cast<int64_t>(nsplit) * kSWarps) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                if (c0 + k < cols) acc[k] += ld1<XT>(x + r * cols + c0 + k);
+                if (c0 + k < cols) {
+                    float v = ld1<XT>(x + r * cols + c0 + k);
+                    if (MASK) {
+                        v = ld1<XT>(act + r * cols + c0 + k) > 0.f ? v : 0.f;
+                        st1<XT>(dz + r * cols + c0 + k, v);
+                    }
+                    acc[k] += v;
+                }
         }
     }
 #pragma unroll
@@ -116,30 +144,52 @@ extern "C" int64_t frl_colsum_scratch_bytes(int64_t rows, int64_t cols) {
            tiles * kSMaxSplits * kSCols * static_cast<int64_t>(sizeof(float));
 }
 
-extern "C" int frl_colsum(const void* x, int x_dtype, int64_t rows, int64_t cols, void* out,
-                          int out_dtype, int accumulate, void* scratch, void* stream) {
-    FRL_REQUIRE(x && out && scratch && rows >= 0 && cols >= 1, FRL_E_ARG, "frl_colsum: bad args");
+static int launch_colsum(const void* x, const void* act, void* dz, int x_dtype, int64_t rows, int64_t cols,
+                         void* out, int out_dtype, int accumulate, void* scratch, void* stream,
+                         const char* name) {
+    FRL_REQUIRE(x && out && scratch && rows >= 0 && cols >= 1, FRL_E_ARG, "%s: bad args", name);
     FRL_REQUIRE((x_dtype == FRL_F32 || x_dtype == FRL_BF16) && (out_dtype == FRL_F32 || out_dtype == FRL_BF16),
-                FRL_E_DTYPE, "frl_colsum: dtype");
+                FRL_E_DTYPE, "%s: dtype", name);
+    const bool mask = act != nullptr;
+    FRL_REQUIRE(!mask || dz != nullptr, FRL_E_ARG, "%s: dz is required with act", name);
     const int64_t tiles = colsum_tiles(cols);
     const int splits = colsum_splits(rows, tiles);
     unsigned int* tickets = static_cast<unsigned int*>(scratch);
     float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +
                                               ((tiles * sizeof(unsigned int) + 15) / 16) * 16);
-    const bool vec = (cols % 8 == 0) && aligned16(x);
+    const bool vec = (cols % 8 == 0) && aligned16(x) && (!mask || (aligned16(act) && aligned16(dz)));
     dim3 grid(static_cast<unsigned int>(tiles), static_cast<unsigned int>(splits));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define FRL_CS(XT, OT)                                                                              \
-    do {                                                                                            \
-        if (vec) colsum_kernel<XT, OT, true><<<grid, kSThreads, 0, st>>>(                          \
-                static_cast<const XT*>(x), rows, cols, static_cast<OT*>(out), accumulate, tickets, partial); \
-        else colsum_kernel<XT, OT, false><<<grid, kSThreads, 0, st>>>(                             \
-                static_cast<const XT*>(x), rows, cols, static_cast<OT*>(out), accumulate, tickets, partial); \
+#define FRL_CS2(XT, OT, V, M)                                                                        \
+    colsum_kernel<XT, OT, V, M><<<grid, kSThreads, 0, st>>>(                                         \
+        static_cast<const XT*>(x), static_cast<const XT*>(act), static_cast<XT*>(dz), rows, cols,    \
+        static_cast<OT*>(out), accumulate, tickets, partial)
+#define FRL_CS(XT, OT)                                                                               \
+    do {                                                                                             \
+        if (vec && mask) FRL_CS2(XT, OT, true, true);                                                \
+        else if (vec) FRL_CS2(XT, OT, true, false);                                                  \
+        else if (mask) FRL_CS2(XT, OT, false, true);                                                 \
+        else FRL_CS2(XT, OT, false, false);                                                          \
     } while (0)
     if (x_dtype == FRL_F32 && out_dtype == FRL_F32) FRL_CS(float, float);
     else if (x_dtype == FRL_BF16 && out_dtype == FRL_BF16) FRL_CS(__nv_bfloat16, __nv_bfloat16);
     else if (x_dtype == FRL_BF16 && out_dtype == FRL_F32) FRL_CS(__nv_bfloat16, float);
     else FRL_CS(float, __nv_bfloat16);
 #undef FRL_CS
-    return after_launch("frl_colsum");
+#undef FRL_CS2
+    return after_launch(name);
+}
+
+extern "C" int frl_colsum(const void* x, int x_dtype, int64_t rows, int64_t cols, void* out,
+                          int out_dtype, int accumulate, void* scratch, void* stream) {
+    return launch_colsum(x, nullptr, nullptr, x_dtype, rows, cols, out, out_dtype, accumulate, scratch,
+                         stream, "frl_colsum");
+}
+
+extern "C" int frl_drelu_colsum(const void* dy, const void* act, void* dz, int dtype, int64_t rows,
+                                int64_t cols, void* out, int out_dtype, int accumulate, void* scratch,
+                                void* stream) {
+    FRL_REQUIRE(act && dz, FRL_E_ARG, "frl_drelu_colsum: act and dz are required");
+    return launch_colsum(dy, act, dz, dtype, rows, cols, out, out_dtype, accumulate, scratch, stream,
+                         "frl_drelu_colsum");
 }

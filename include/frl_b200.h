@@ -167,6 +167,12 @@ int frl_cast_scale(const void* src, int src_dtype, void* dst, int dst_dtype, int
 int64_t frl_colsum_scratch_bytes(int64_t rows, int64_t cols);
 int frl_colsum(const void* x, int x_dtype, int64_t rows, int64_t cols, void* out, int out_dtype,
                int accumulate, void* scratch, void* stream);
+/* K6b — the same pass with ReLU's backward folded in, for a Linear+ReLU pair: dz[r,c] =
+ * act[r,c] > 0 ? dy[r,c] : 0 (act = the layer's forward output; dy, act, dz share dtype and the
+ * [rows, cols] layout; dz may alias dy) and out[c] (+)= sum_r dz[r,c].  Replaces autograd's
+ * threshold_backward kernel plus the bias-gradient reduction (reference solver_worker.py:586). */
+int frl_drelu_colsum(const void* dy, const void* act, void* dz, int dtype, int64_t rows, int64_t cols,
+                     void* out, int out_dtype, int accumulate, void* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K7 — fused gradient all-reduce + optimizer update + weight broadcast over NVSwitch multicast

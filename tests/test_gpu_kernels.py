@@ -474,3 +474,74 @@ def test_tma_gather_rejects_rows_that_are_not_multiples_of_16_bytes():
     with pytest.raises(_native.NativeLibraryError):
         _native.gather_rows_tma(src, torch.zeros(2, dtype=torch.int64, device=DEV),
                                 torch.zeros(2, 3, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------------
+# K6b + Linear/ReLU units (FRL_B200_FUSE_RELU)
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (7, 13), (4096, 4096), (333, 264), (5, 4104)])
+@pytest.mark.parametrize("xdt,odt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                     (torch.bfloat16, torch.float32)])
+def test_drelu_colsum_matches_threshold_backward_plus_sum(rows, cols, xdt, odt):
+    dy = torch.randn(rows, cols, device=DEV).to(xdt)
+    act = torch.relu(torch.randn(rows, cols, device=DEV)).to(xdt)          # ~half zeros, as a ReLU output
+    dz = torch.full_like(dy, 7.0)
+    out = torch.full((cols,), 3.0, dtype=odt, device=DEV)
+    _native.drelu_colsum(dy, act, dz, out)
+    want_dz = torch.where(act > 0, dy, torch.zeros_like(dy))                # aten threshold_backward
+    assert torch.equal(dz, want_dz)                                        # a select: exact
+    want = want_dz.double().sum(0)
+    tol = dict(rtol=2e-2, atol=2e-1) if odt == torch.bfloat16 else dict(rtol=1e-5, atol=1e-4 * max(rows, 1) ** 0.5)
+    torch.testing.assert_close(out.double(), want, **tol)
+    before = out.clone()
+    _native.drelu_colsum(dy, act, dz, out, accumulate=True)
+    torch.testing.assert_close(out.double(), before.double() + want, **tol)
+    # in place (dz aliasing dy) gives the same result
+    dy2 = dy.clone()
+    _native.drelu_colsum(dy2, act, dy2, out)
+    assert torch.equal(dy2, want_dz)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_linear_relu_units_match_the_unfused_modules(precision, monkeypatch):
+    import torch.nn as nn
+    from frl_b200 import fused_optim, grad_sync
+    from frl_b200.arena import ParamArena
+    from frl_b200.types import OptAlgorithm, OptimOpts, Precision
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def build():
+        torch.manual_seed(0)
+        shared = nn.ReLU()
+        return nn.Sequential(nn.Linear(40, 64), nn.ReLU(), nn.Linear(64, 64), nn.ReLU(inplace=True),
+                             nn.Linear(64, 32), shared, nn.Linear(32, 32), shared, nn.Linear(32, 8)).to(DEV)
+    prec = Precision(precision)
+    x0 = torch.randn(3, 32, 40, device=DEV)               # 3-D input: units must keep leading dims
+    results = []
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("FRL_B200_FUSE_RELU", fuse)
+        net = build()
+        arena = ParamArena(net.parameters(), device=DEV, precision=prec)
+        opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm.SGD, lr=0.05))
+        pipe = grad_sync.GradBucketPipeline(arena, opt, bucket_cap_mb=0.004, eager_update=True)
+        assert pipe.patch_linears(net) == 5
+        fused = [s.relu is not None for s in pipe.linear_sites]
+        assert fused == ([True, True, False, False, False] if fuse == "1" else [False] * 5)  # shared ReLU: left alone
+        x = x0.to(torch.bfloat16) if prec == Precision.BF16 else x0
+        outs = []
+        for _ in range(3):
+            pipe.begin_step()
+            y = net(x)
+            outs.append(y.detach().float().clone())
+            y.float().square().mean().backward()
+            pipe.finish_step()
+        torch.cuda.synchronize()
+        results.append((arena.grad.float().clone(), arena.master.clone(), outs))
+        pipe.remove_hooks()
+        assert all("forward" not in m.__dict__ for m in net)          # everything unpatched again
+    tol = dict(rtol=2e-2, atol=2e-3) if prec == Precision.BF16 else dict(rtol=1e-4, atol=1e-6)
+    for a, b in zip(results[1][2], results[0][2]):
+        torch.testing.assert_close(a, b, **tol)
+    torch.testing.assert_close(results[1][0], results[0][0], **tol)
+    torch.testing.assert_close(results[1][1], results[0][1], **tol)

@@ -305,3 +305,26 @@ def test_batched_input_path_with_a_ragged_last_batch(ns, monkeypatch, path):
         assert pa.nSamples == pb.nSamples
         for k in pa.metrics:
             assert pb.metrics[k] == pytest.approx(pa.metrics[k], rel=1e-6, abs=1e-8)
+
+
+@pytest.mark.parametrize("graph", ["0", "1"])
+def test_fused_linear_relu_units_keep_reference_parity(ns, golden_dir, monkeypatch, graph):
+    """FRL_B200_FUSE_RELU=1: the toy trunk's two Linear+ReLU pairs run as cuBLASLt bias+ReLU
+    GEMMs with dReLU folded into the bias-gradient pass; same parity bar against the reference
+    run, eager and under CUDA-graph replay, and the checkpointed module is a plain one."""
+    monkeypatch.setenv("FRL_B200_FUSE_RELU", "1")
+    monkeypatch.setenv("FRL_B200_CUDA_GRAPH", graph)
+    g = np.load(os.path.join(golden_dir, "toy_sgd.npz"))
+    _, worker, problem, save_dir = _solve_and_capture(ns, CONFIGS["toy_sgd"])
+    assert sum(s.relu is not None for s in worker.pipeline.linear_sites) == 2
+    rows = np.concatenate([r for _, _, r in worker.loss_history])
+    np.testing.assert_allclose(rows, g["rows"], rtol=1e-5, atol=1e-6)
+    final = torch.load(os.path.join(save_dir, "final_model.pth"), weights_only=False)
+    for i, k in enumerate(list(g["param_names"])):
+        np.testing.assert_allclose(final["state_dict"][k].numpy(), g["param_%02d" % i], rtol=2e-4, atol=2e-6)
+    whole = torch.load(os.path.join(save_dir, "final_model.pth.model"), weights_only=False)
+    x = torch.rand(5, 64)
+    with torch.no_grad():
+        out = whole([x])                                   # pickled module: stock forward, ReLUs active
+    assert all("forward" not in m.__dict__ for m in whole.modules())
+    assert len(out) == 2 and out[0].shape == (5, 4)
