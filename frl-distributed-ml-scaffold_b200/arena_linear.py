@@ -15,7 +15,7 @@ so the bucket NCCL reduces is complete the moment the layer's backward returns: 
 copy, no separate bias-reduction pass through a generic reduce kernel.  Outside a pipeline
 step (``autograd.grad`` calls of GradNorm / debugGrad) the Function returns ordinary gradients.
 
-``FRL_B200_FUSE_RELU=1``: a ``nn.Linear`` directly followed by a ``nn.ReLU`` inside a
+Unless ``FRL_B200_FUSE_RELU=0``, a ``nn.Linear`` directly followed by a ``nn.ReLU`` inside a
 ``nn.Sequential`` (each module used exactly once, no hooks) runs as one unit:
 
   forward   y = relu(x W^T + b)                one cuBLASLt GEMM with the bias+ReLU epilogue
@@ -45,7 +45,18 @@ class _ArenaLinearFn(torch.autograd.Function):
         ctx.site = site
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight)
-        return F.linear(x, weight, bias)
+        if x.dim() <= 2:
+            return F.linear(x, weight, bias)
+        # N-D input: F.linear would return a VIEW of its 2-D result, and autograd forbids in-place
+        # ops (nn.ReLU(inplace=True)) on a view created inside a custom Function: write the GEMM
+        # into a 2-D view of a fresh N-D tensor instead and return that tensor
+        y = torch.empty(*x.shape[:-1], weight.shape[0], dtype=x.dtype, device=x.device)
+        x2 = x.reshape(-1, x.shape[-1])
+        if bias is not None:
+            torch.addmm(bias, x2, weight.t(), out=y.view(-1, weight.shape[0]))
+        else:
+            torch.mm(x2, weight.t(), out=y.view(-1, weight.shape[0]))
+        return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -85,8 +96,9 @@ class _ArenaLinearReluFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, site):
         ctx.site = site
         x2 = x.reshape(-1, x.shape[-1])
-        y2 = torch._addmm_activation(bias, x2, weight.t(), use_gelu=False)
-        y = y2.view(*x.shape[:-1], weight.shape[0])
+        # the output must not be a view (see _ArenaLinearFn.forward): GEMM into a view of it
+        y = torch.empty(*x.shape[:-1], weight.shape[0], dtype=x.dtype, device=x.device)
+        torch._addmm_activation(bias, x2, weight.t(), use_gelu=False, out=y.view(-1, weight.shape[0]))
         ctx.save_for_backward(x, weight, y)
         return y
 
@@ -191,7 +203,7 @@ def patch_linears(model: nn.Module, pipeline) -> List[LinearSite]:
             continue                     # frozen bias: leave the module alone
         site = LinearSite(mod, wslot, bslot, pipeline)
         sites.append(site)
-    if os.environ.get("FRL_B200_FUSE_RELU", "0") != "0":
+    if os.environ.get("FRL_B200_FUSE_RELU", "1") != "0":
         _fuse_relu_pairs(model, sites)
     repatch_linears(sites)
     return sites

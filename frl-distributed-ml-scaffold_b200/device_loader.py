@@ -15,19 +15,23 @@ arithmetic runs once per batch on the device (``frl_preproc_affine``).
 
 Three ways to move the rows (``FRL_B200_INPUT_PATH``):
 
+``kernel`` (default) ``frl_gather_rows``: 16 small CTAs (256 threads, no shared memory) pull the rows
+                    over PCIe with 16-byte LSU loads on a high-priority copy stream — no host CPU
+                    work, no staging copy in host DRAM;
+``tma``             ``frl_gather_rows_tma``: the same with ``cp.async.bulk`` through 2 CTAs;
 ``host``            native worker threads (``frl_gather_pool_*``) copy the rows of batch *k+2* into
                     a pinned staging buffer, the copy engine moves batch *k+1* to HBM as one
-                    contiguous DMA per field, the SMs see nothing of it;
-``tma``             ``frl_gather_rows_tma``: a few CTAs pull the rows over PCIe with
-                    ``cp.async.bulk`` (no host CPU work, no staging copy in host DRAM);
-``kernel``          ``frl_gather_rows``: the same with LSU loads.
+                    contiguous DMA per field, the SMs see nothing of it.  The only path for
+                    sources that are not pinned (memory-mapped ``.bin`` files), and the only one
+                    that can ship bf16 over PCIe (``FRL_B200_INPUT_WIRE=bf16``).
 
 Measured on B200 (round 1): every path reaches PCIe speed (51-55 GB/s, 1.2-1.3 ms for a 67 MB
-batch) when run alone, but CTAs that occupy SMs for that long slow the step's cluster-scheduled
-GEMMs by ~35 %, so ``host`` is the default for one rank per node.  It costs host DRAM 3x the PCIe
-payload, which several ranks on one socket cannot afford (2 ranks: 3.8 ms/step, 8 ranks: 4.3 vs 2.0
-for the SM paths): ``auto`` switches to
-``kernel`` there, whose CTAs are small enough to share SMs with the GEMM CTAs.
+batch) when run alone.  Under the training step, CTAs that occupy SMs for that long slow the
+cluster-scheduled GEMMs: the TMA kernel's 128 KB of staging evicts a GEMM CTA per CTA (2.1 ms/step
+end to end), the LSU kernel's CTAs fit beside them (1.53 with 16 CTAs; 1.69 with 8, 1.80 with 32).
+The host path is the fastest on a quiet single-GPU node (1.47) and the most fragile: 3x the
+payload in host DRAM traffic and 16-24 busy threads — 3.8 ms/step with two ranks on a socket, 4.3
+with eight, and 1.7 to 5.5 on a shared host depending on the neighbours.
 """
 from collections import deque
 from typing import Dict, Iterator, List, Optional, Tuple
@@ -75,15 +79,18 @@ def _local_world() -> int:
 
 
 def default_input_path() -> str:
-    """``host`` while the ranks of this node are few enough for host DRAM to carry the staging
-    copy (3x the PCIe payload: gather read + staging write + DMA read), else ``kernel`` (1x).
+    """``kernel`` everywhere: it needs nothing from the host but PCIe reads.  ``host`` is faster by
+    ~5 % when ONE rank has the node's CPUs and DRAM to itself (1.47 vs 1.53 ms/step), but it costs
+    host DRAM 3x the PCIe payload (gather read + staging write + DMA read) and 16-24 busy threads:
+    two ranks on one socket already lose (3.8 ms/step), and on a shared host its speed follows the
+    neighbours' load (same box, same day: 1.70 and 5.5 ms/step through the public loop).
     Measured, 67 MB fp32 batches, ms/step end to end: 1 x B200 host 1.47 | kernel (16 CTAs) 1.53 |
     kernel (8) 1.69 | tma (2 CTAs) 2.08 | tma (8) 2.85; 2 x B200 (one socket) host 3.8;
     4 x B200 host 2.47 | tma 2.03;
     8 x B200 host 4.3 | tma 2.0 (the box's aggregate H2D rate, ~270 GB/s, is the floor there).
     The LSU kernel's CTAs (256 threads, no shared memory) fit beside the GEMM CTAs on an SM; the
     TMA kernel's 128 KB of staging does not, so each of its CTAs takes an SM from the GEMMs."""
-    return "host" if _local_world() <= 1 else "kernel"
+    return "kernel"
 
 
 def default_gather_threads() -> int:

