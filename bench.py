@@ -172,7 +172,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:                       # noqa: BLE001
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.004)
 
     def __enter__(self):
         if self._nv is not None:
