@@ -210,6 +210,7 @@ class DeviceBatchLoader:
         s = k % self.depth
         slot = self._slots[s]
         n = idx.numel()
+        self._ready[s].synchronize()      # the slot's previous index upload has left the pinned row
         slot["__idx_host"][:n].copy_(idx)
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(self._freed[s])          # previous user of the slot is done
