@@ -314,3 +314,47 @@ def test_host_pool_bf16_wire_conversion_is_bit_identical_to_torch():
     with pytest.raises(_native.NativeLibraryError):
         pool.submit_f32_to_bf16(small, torch.tensor([50]), out2)
     pool.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# hang guard (reference tests/test_watchdog_timer.py restated for the one-thread-per-loop guard)
+# ------------------------------------------------------------------------------------------------
+
+def test_watchdog_completes_quietly_and_stops_its_thread():
+    import threading
+    import time
+    from frl_b200.watchdog import StepWatchdog
+    before = threading.active_count()
+    with StepWatchdog(1_000_000) as dog:                    # reference: test_timer_completes
+        assert dog._thread is not None and dog._thread.is_alive()
+        for _ in range(5):
+            dog.kick()
+    dog._thread.join(timeout=3)
+    assert not dog._thread.is_alive() and not dog.fired
+    assert threading.active_count() <= before
+
+
+def test_watchdog_expires_with_timeout_error_in_the_guarded_thread():
+    import time
+    from frl_b200.watchdog import StepWatchdog
+    with pytest.raises(TimeoutError):                       # reference: test_timer_expires_with_exception
+        with StepWatchdog(0):
+            time.sleep(1)
+            for _ in range(100):                            # async exceptions land between bytecodes
+                time.sleep(0.01)
+
+
+def test_watchdog_kicks_postpone_the_deadline_and_a_stall_fires_it():
+    import time
+    from frl_b200.watchdog import StepWatchdog
+    with StepWatchdog(300) as dog:
+        for _ in range(8):                                  # 0.8 s of work, never 300 ms without a kick
+            time.sleep(0.1)
+            dog.kick()
+        assert not dog.fired
+    with pytest.raises(TimeoutError):
+        with StepWatchdog(200) as dog:
+            dog.kick()
+            for _ in range(300):                            # a "hung minibatch": no kick for > 200 ms
+                time.sleep(0.01)
+    assert dog.fired
