@@ -305,3 +305,56 @@ def test_criterion_classes_match_live_reference(kind):
         assert list(ms) == list(rs) and all(torch.equal(ms[k], rs[k]) for k in rs)
         assert len(mg) == len(rg) and all(torch.equal(a, b) for a, b in zip(mg, rg))
     assert all(torch.equal(a, b) for a, b in zip(my_params, ref_params))
+
+
+# ------------------------------------------------------------------------------------------------
+# parent-side aggregation of the per-rank epoch summaries (reference solver.py:457-526): sample-
+# weighted means over ranks, MSE -> RMSE renaming, invalid (negative) metrics passed through
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.reference
+def test_rank_aggregation_matches_live_reference():
+    from oracle.ref_shim import import_reference
+    import_reference()
+    import frldistml.scaffold.solver as ref_solver
+    import frldistml.scaffold.solver_worker as ref_sw
+    import frldistml.scaffold.types as ref_t
+    import frl_b200  # noqa: F401
+    import frl_b200.solver as my_solver
+    import frl_b200.solver_worker as my_sw
+    import frl_b200.types as my_t
+
+    per_rank = [   # (nSamples, losses, metrics) per split, three ranks with unequal sample counts
+        {"training": (100, {"reg": 0.5, "cls": 2.25}, {"reg_MSE": 0.04, "cls_err": 0.25, "pose_MSE_deg": 9.0}),
+         "testing": (10, {"reg": 0.7, "cls": 2.0}, {"reg_MSE": 0.09, "cls_err": 0.5, "pose_MSE_deg": -1.0})},
+        {"training": (60, {"reg": 0.25, "cls": 1.75}, {"reg_MSE": 0.01, "cls_err": 0.125, "pose_MSE_deg": 4.0}),
+         "testing": (30, {"reg": 0.1, "cls": 3.0}, {"reg_MSE": 0.16, "cls_err": 0.75, "pose_MSE_deg": -1.0})},
+        {"training": (7, {"reg": 1.5, "cls": 0.5}, {"reg_MSE": 0.25, "cls_err": 1.0, "pose_MSE_deg": 1.0}),
+         "testing": (3, {"reg": 0.3, "cls": 1.0}, {"reg_MSE": 0.0, "cls_err": 0.0, "pose_MSE_deg": -1.0})},
+    ]
+
+    def run(solver_mod, sw_mod, t):
+        class DS:
+            def __init__(self, split):
+                self.data_type = split
+
+        class P:
+            datasets = [DS(t.Split.TRAIN), DS(t.Split.TEST)]
+
+        fracs = []
+        for rank in per_rank:
+            perf = {t.Split(name): sw_mod.FractionalEpochSplitPerformanceSummary(
+                        nSamples=n, losses=dict(losses), metrics=dict(metrics), samples=[],
+                        worstSamples=[], testIO=[])
+                    for name, (n, losses, metrics) in rank.items()}
+            fracs.append(sw_mod.FractionalPerformanceSummary(
+                epoch=3, modelBuffer=b"", optimizerStateBuffer=b"", performance=perf))
+        ro = t.RunOpts(optim=t.OptimOpts(algo=t.OptAlgorithm.SGD), batchSize=4)
+        out = solver_mod.Solver._aggregate_fractional_results(ro, P(), fracs)
+        return {split.value: (dict(s.losses), dict(s.metrics)) for split, s in out.items()}
+
+    want = run(ref_solver, ref_sw, ref_t)
+    got = run(my_solver, my_sw, my_t)
+    assert got == want
+    assert set(want["training"][1]) == {"reg_RMSE", "cls_err", "pose_RMSE_deg"}
+    assert want["testing"][1]["pose_RMSE_deg"] == -1.0          # invalid metric: not square-rooted
