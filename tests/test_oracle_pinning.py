@@ -358,3 +358,94 @@ def test_rank_aggregation_matches_live_reference():
     assert got == want
     assert set(want["training"][1]) == {"reg_RMSE", "cls_err", "pose_RMSE_deg"}
     assert want["testing"][1]["pose_RMSE_deg"] == -1.0          # invalid metric: not square-rooted
+
+
+# ------------------------------------------------------------------------------------------------
+# checkpoint files written by the parent (reference solver.py:565-651): same four files, same
+# contents, and each side's loader reads the other's checkpoint
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.reference
+def test_checkpoint_files_match_live_reference(tmp_path):
+    import io
+    from typing import NamedTuple
+    from oracle.ref_shim import import_reference
+    import_reference()
+    import frldistml.scaffold.solver as ref_solver
+    import frldistml.scaffold.solver_worker as ref_sw
+    import frldistml.scaffold.types as ref_t
+    from frldistml.scaffold.storage import StoragePath
+    import frl_b200  # noqa: F401
+    import frl_b200.solver as my_solver
+    import frl_b200.solver_worker as my_sw
+    import frl_b200.types as my_t
+
+    torch.manual_seed(1)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.BatchNorm1d(5), torch.nn.ReLU(),
+                                torch.nn.Linear(5, 3))
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-5)
+    for _ in range(3):
+        opt.zero_grad()
+        model(torch.randn(8, 6)).square().mean().backward()
+        opt.step()
+    model.eval()
+    buf = io.BytesIO()
+    torch.save(model, buf)
+    model_bytes = buf.getvalue()
+    buf = io.BytesIO()
+    torch.save(opt.state_dict(), buf)
+    optim_bytes = buf.getvalue()
+    samples = [dict(data=[torch.randn(6)], target=[(torch.randn(3),)], meta={"index": torch.tensor(i)},
+                    output=[torch.randn(3)], metric={"m": 0.5}) for i in range(2)]
+
+    class Anno(NamedTuple):
+        scale: float = 2.0
+        names: tuple = ("a", "b")
+
+    class P:
+        anno_param = Anno()
+
+    def write(solver_mod, sw_mod, t, save_dir):
+        io_samples = [sw_mod.SingleSample(**s) for s in samples]
+        perf = {t.Split.TRAIN: sw_mod.FractionalEpochSplitPerformanceSummary(
+                    nSamples=10, losses={}, metrics={}, samples=[], worstSamples=[], testIO=[]),
+                t.Split.TEST: sw_mod.FractionalEpochSplitPerformanceSummary(
+                    nSamples=4, losses={}, metrics={}, samples=[], worstSamples=[], testIO=io_samples)}
+        frac = sw_mod.FractionalPerformanceSummary(epoch=7, modelBuffer=model_bytes,
+                                                   optimizerStateBuffer=optim_bytes, performance=perf)
+        ro = t.RunOpts(optim=t.OptimOpts(algo=t.OptAlgorithm.SGD), batchSize=4)
+        solver_mod.Solver._save_checkpoint(7, save_dir, ro, P(), [frac], ".checkpoint.pth")
+
+    ref_dir, my_dir = tmp_path / "ref", tmp_path / "mine"
+    ref_dir.mkdir()
+    my_dir.mkdir()
+    write(ref_solver, ref_sw, ref_t, StoragePath(str(ref_dir)))
+    write(my_solver, my_sw, my_t, str(my_dir))
+    names = sorted(os.listdir(ref_dir))
+    assert sorted(os.listdir(my_dir)) == names == [".checkpoint.pth", ".checkpoint.pth.annotate_param",
+                                                   ".checkpoint.pth.model", ".checkpoint.pth.test_data"]
+
+    def same(a, b):
+        if torch.is_tensor(a):
+            return torch.is_tensor(b) and a.dtype == b.dtype and torch.equal(a, b)
+        if isinstance(a, dict):
+            return isinstance(b, dict) and list(a) == list(b) and all(same(a[k], b[k]) for k in a)
+        if isinstance(a, (list, tuple)):
+            return type(a) is type(b) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        return a == b
+
+    for n in (".checkpoint.pth", ".checkpoint.pth.test_data", ".checkpoint.pth.annotate_param"):
+        a = torch.load(os.path.join(ref_dir, n), weights_only=False)
+        b = torch.load(os.path.join(my_dir, n), weights_only=False)
+        assert same(a, b), n
+    whole_ref = torch.load(os.path.join(ref_dir, ".checkpoint.pth.model"), weights_only=False)
+    whole_mine = torch.load(os.path.join(my_dir, ".checkpoint.pth.model"), weights_only=False)
+    assert same(dict(whole_ref.state_dict()), dict(whole_mine.state_dict()))
+    # each loader reads the other side's file
+    with open(os.path.join(my_dir, ".checkpoint.pth"), "rb") as f:
+        got = ref_solver.Solver._load_checkpoint(f)
+    with open(os.path.join(ref_dir, ".checkpoint.pth"), "rb") as f:
+        back = my_solver.Solver._load_checkpoint(f)
+    assert got.epoch == back.epoch == 7
+    assert same(dict(got.modelState), dict(back.modelState)) and same(got.optimizerState, back.optimizerState)
+    torch.optim.SGD(whole_mine.parameters(), lr=0.1, momentum=0.9).load_state_dict(got.optimizerState)
