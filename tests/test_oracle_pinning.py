@@ -449,3 +449,41 @@ def test_checkpoint_files_match_live_reference(tmp_path):
     assert got.epoch == back.epoch == 7
     assert same(dict(got.modelState), dict(back.modelState)) and same(got.optimizerState, back.optimizerState)
     torch.optim.SGD(whole_mine.parameters(), lr=0.1, momentum=0.9).load_state_dict(got.optimizerState)
+
+
+@pytest.mark.reference
+def test_initial_model_loading_matches_live_reference(tmp_path, capsys):
+    """``initialModelPath`` (reference solver.py:122-159): strict load, and the partial load that
+    copies what matches in name and shape and reports the rest — same weights, same messages."""
+    from oracle.ref_shim import import_reference
+    import_reference()
+    import frldistml.scaffold.solver as ref_solver
+    import frl_b200  # noqa: F401
+    import frl_b200.solver as my_solver
+
+    def net(width):
+        torch.manual_seed(width)
+        return torch.nn.Sequential(torch.nn.Linear(4, width), torch.nn.ReLU(), torch.nn.Linear(width, 2))
+
+    donor = net(5)
+    state = dict(donor.state_dict())
+    state["extra.weight"] = torch.ones(3)
+    state["0.weight"] = torch.nn.Parameter(state["0.weight"].clone())      # legacy serialised Parameter
+    path = str(tmp_path / "init.pth")
+    torch.save({"state_dict": state}, path)
+    results = []
+    for mod in (ref_solver, my_solver):
+        target = net(5)
+        del_key = net(7)                       # different width: shape mismatches on every tensor but one
+        mod._load_model_state(target, path, strict=False)
+        mod._load_model_state(del_key, path, strict=False)
+        out = capsys.readouterr().out
+        lines = [l for l in out.splitlines() if l.startswith("Warning")]
+        results.append((dict(target.state_dict()), dict(del_key.state_dict()), lines))
+        with pytest.raises(RuntimeError):
+            mod._load_model_state(net(5), path, strict=True)               # unexpected key "extra.weight"
+        capsys.readouterr()
+    (ra, rb, rl), (ma, mb, ml) = results
+    assert all(torch.equal(ra[k], ma[k]) for k in ra) and all(torch.equal(rb[k], mb[k]) for k in rb)
+    assert ml == rl and len(rl) >= 4
+    assert torch.equal(ma["0.weight"], donor.state_dict()["0.weight"])
