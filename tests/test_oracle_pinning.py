@@ -487,3 +487,54 @@ def test_initial_model_loading_matches_live_reference(tmp_path, capsys):
     assert all(torch.equal(ra[k], ma[k]) for k in ra) and all(torch.equal(rb[k], mb[k]) for k in rb)
     assert ml == rl and len(rl) >= 4
     assert torch.equal(ma["0.weight"], donor.state_dict()["0.weight"])
+
+
+@pytest.mark.reference
+def test_multitask_problem_plumbing_matches_live_reference():
+    """The same synthetic MultiTaskProblem source instantiated against this package and against
+    the reference (Problem/MultiTaskProblem/MultiTaskTransform/Task/MultiTaskModel):
+    per-sample items, model structure and initial weights, criterion composition, merged metric
+    hooks and rankable metric must coincide."""
+    from oracle.ref_shim import import_reference
+    import_reference()
+    import frl_b200  # noqa: F401
+    from frl_b200 import synthetic
+    built = {}
+    for pkg in ("frldistml.scaffold", "frl_b200"):
+        ns = synthetic.api_namespace(pkg)
+        problem = synthetic.make_toy_problem(ns, "/tmp/unused")
+        torch.manual_seed(21)
+        model = problem.get_model()
+        crit = problem.get_criterion()
+        items = [problem.datasets[0][i] for i in (0, 5, 511)] + [problem.datasets[1][3]]
+        g = torch.Generator().manual_seed(2)
+        out = [torch.randn(6, 4, generator=g), torch.randn(6, 10, generator=g)]
+        tgt = [(torch.randn(6, 4, generator=g),), (torch.randint(0, 10, (6,), generator=g),)]
+        meta = problem.refine_batch_meta({"index": torch.arange(6)})
+        metrics = problem.compute_batch_metrics(meta=meta, target=tgt, output=out, device=torch.device("cpu"))
+        with torch.no_grad():
+            y = model([torch.ones(2, 64)])
+        built[pkg] = dict(
+            model_type=type(model).__name__, crit_type=type(crit).__name__,
+            state={k: v.clone() for k, v in model.state_dict().items()},
+            names=list(crit.loss_names), weights=[float(w) for w in crit.loss_weights],
+            loss_mods=[type(m).__name__ for m in crit.loss_modules], items=items,
+            metrics={k: np.asarray(v) for k, v in metrics.items()},
+            rank=(problem.get_rankable_metric()[0], problem.get_rankable_metric()[1].name),
+            epoch=problem.summarize_epoch_metrics({k: np.asarray(v) for k, v in metrics.items()}),
+            meta_fields=meta._fields, y=[t.clone() for t in y],
+            splits=[d.data_type.value for d in problem.datasets], lens=[len(d) for d in problem.datasets])
+    ref, mine = built["frldistml.scaffold"], built["frl_b200"]
+    for k in ("model_type", "crit_type", "names", "weights", "loss_mods", "rank", "epoch", "meta_fields",
+              "splits", "lens"):
+        assert mine[k] == ref[k], k
+    assert list(mine["state"]) == list(ref["state"])
+    assert all(torch.equal(mine["state"][k], ref["state"][k]) for k in ref["state"])
+    assert all(torch.equal(a, b) for a, b in zip(mine["y"], ref["y"]))
+    assert all(np.array_equal(mine["metrics"][k], ref["metrics"][k]) for k in ref["metrics"])
+    for a, b in zip(mine["items"], ref["items"]):
+        assert len(a) == len(b) == 3
+        assert all(torch.equal(x, y) for x, y in zip(a[0], b[0]))                      # data list
+        assert all(torch.equal(x[0], y[0]) for x, y in zip(a[1], b[1]))                # target tuples
+        assert list(a[2]) == list(b[2]) and all(torch.equal(torch.as_tensor(a[2][k]), torch.as_tensor(b[2][k]))
+                                                 for k in a[2])
