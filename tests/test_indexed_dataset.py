@@ -227,3 +227,52 @@ def test_batched_access_refuses_ragged_files(tmp_path):
     assert len(r) == 2 and r[0].shape == (2, 3)               # per-sample reads keep working (frame-0 shape)
     with pytest.raises(ValueError, match="fixed-size frames"):
         r.frames_tensor()
+
+
+# ---- Concat / Subset containers over indexed datasets (reference dataset.py:518-552) ---------------
+
+@pytest.mark.reference
+def test_concat_and_subset_containers_match_the_live_reference(tmp_path):
+    from oracle.ref_shim import import_reference
+    import_reference()
+    import frldistml.scaffold.storage_layers.dataset as ref_ds
+    from frldistml.scaffold.indexed_dataset import MultifieldIndexedDataset as RefMulti
+    from frldistml.scaffold.storage import StoragePath
+    import frl_b200.storage_layers.dataset as my_ds
+    rs = np.random.RandomState(9)
+    sizes = [5, 1, 7]
+    for k, n in enumerate(sizes):
+        idm.write_fields(str(tmp_path / ("part%d" % k)),
+                         {"a": rs.randn(n, 3).astype(np.float32), "b": rs.randint(0, 9, (n, 2)).astype(np.int64)})
+
+    class Recorder:
+        def __init__(self, log, offset=0, field=None):
+            self.log, self.offset, self.field = log, offset, field
+
+        def with_dataset_global_offset(self, offset):
+            return Recorder(self.log, offset, self.field)
+
+        def with_multifield_dataset_field(self, field):
+            self.log.append((self.offset, field))
+            return Recorder(self.log, self.offset, field)
+
+    mine_parts = [idm.MultifieldIndexedDataset(str(tmp_path / ("part%d" % k)), fields=["a", "b"], filenames=["a", "b"])
+                  for k in range(3)]
+    ref_parts = [RefMulti(StoragePath(str(tmp_path / ("part%d" % k))), fields=["a", "b"], filenames=["a", "b"])
+                 for k in range(3)]
+    mine, ref = my_ds.ConcatMultifieldDataset(mine_parts), ref_ds.ConcatMultifieldDataset(ref_parts)
+    assert len(mine) == len(ref) == sum(sizes)
+    for i in range(len(ref)):
+        a, b = mine.get_raw_item(i), ref.get_raw_item(i)
+        assert list(a) == list(b) and all(np.array_equal(a[k], b[k]) and a[k].dtype == b[k].dtype for k in a)
+        c, d = mine[i], ref[i]
+        assert all(np.array_equal(c[k], d[k]) for k in c)
+    log_mine, log_ref = [], []
+    mine.set_accessor(Recorder(log_mine))
+    ref.set_accessor(Recorder(log_ref))
+    assert log_mine == log_ref == [(0, "a"), (0, "b"), (5, "a"), (5, "b"), (6, "a"), (6, "b")]
+    picks = [12, 0, 5, 5, 3]
+    sub_mine, sub_ref = my_ds.SubsetMultifieldDataset(mine, picks), ref_ds.SubsetMultifieldDataset(ref, picks)
+    assert len(sub_mine) == len(sub_ref) == 5
+    for j in range(5):
+        assert all(np.array_equal(sub_mine[j][k], sub_ref[j][k]) for k in ("a", "b"))
