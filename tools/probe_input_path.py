@@ -83,28 +83,29 @@ for blocks in (1, 2, 3, 4, 8):
 for blocks in (2, 4, 8, 16):
     report("frl_gather_rows blocks=%d" % blocks,
            timed(lambda r: _native.gather_rows(src, perms_dev[r], dst, max_blocks=blocks)))
-try:
-    dst.zero_()
-    report("frl_h2d_rows_batch (event time)", timed(lambda r: _native.h2d_rows_batch(src, perms[r], dst)))
-    report("frl_h2d_rows_batch (host wall incl. submit)",
-           timed(lambda r: _native.h2d_rows_batch(src, perms[r], dst), sync_host=True))
-    print("   correct:", torch.equal(dst.cpu(), src[perms[5]]))
-    t0 = time.perf_counter()
-    _native.h2d_rows_batch(src, perms[0], dst)
-    t1 = time.perf_counter()
-    torch.cuda.synchronize()
-    print("   submit cost on the host: %.3f ms" % ((t1 - t0) * 1e3))
-except Exception as e:  # noqa: BLE001
-    print("batch DMA variant failed:", e)
+# (cudaMemcpyBatchAsync with one descriptor per row was measured once and rejected: 7.4 GB/s,
+#  19 ms of host time per 4096-row submission; see profiles/r1b_probe_input_path_b.log)
 stage = torch.empty(B, W).pin_memory()
 for th in (1, 4, 8, 16, 32):
+    pool = _native.HostGatherPool(th)
     t = []
     for r in range(5):
         t0 = time.perf_counter()
-        _native.host_gather_rows(src, perms[r], stage, n_threads=th)
+        pool.wait(pool.submit(src, perms[r], stage))
         t.append(time.perf_counter() - t0)
-    report("frl_host_gather_rows threads=%d (host)" % th, min(t[1:]) * 1e3)
+    pool.close()
+    report("frl_gather_pool threads=%d (host)" % th, min(t[1:]) * 1e3)
 print("   correct:", torch.equal(stage, src[perms[4]]))
+stage16 = torch.empty(B, W, dtype=torch.bfloat16).pin_memory()
+pool = _native.HostGatherPool(16)
+t = []
+for r in range(5):
+    t0 = time.perf_counter()
+    pool.wait(pool.submit_f32_to_bf16(src, perms[r], stage16))
+    t.append(time.perf_counter() - t0)
+pool.close()
+report("frl_gather_pool f32->bf16 wire, 16 threads", min(t[1:]) * 1e3)
+print("   correct:", torch.equal(stage16, src[perms[4]].to(torch.bfloat16)))
 
 # host cost of the index stream (DataLoader + sampler machinery, as DeviceBatchLoader uses it)
 from frl_b200.device_loader import _IndexOnly, _collate_indices  # noqa: E402
