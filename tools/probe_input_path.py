@@ -4,8 +4,9 @@
     python tools/probe_input_path.py [rows_per_batch] [row_elems]
 
 Prints GB/s of: contiguous cudaMemcpyAsync (PCIe reference), frl_gather_rows at several grid
-sizes, frl_gather_rows_tma, frl_h2d_rows_batch, frl_host_gather_rows (+ the DMA that follows),
-and the host cost of drawing one index batch from the DataLoader machinery.
+sizes, frl_gather_rows_tma, the native host gather pool per thread count (plain and with the
+fp32 -> bf16 wire conversion), and the host cost of drawing one index batch from the DataLoader
+machinery.
 """
 import os
 import sys
