@@ -70,19 +70,17 @@ class _ArenaLinearFn(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1])
         pipe = site.pipeline
         if pipe is not None and pipe.step_open:
-            first = site.touched_step != pipe.step_id
-            site.touched_step = pipe.step_id
             gw = pipe.arena.grad_view(site.wslot)
-            if first:
+            if site.wstate.first_touch(pipe.step_id):
                 torch.mm(dy2.t(), x2, out=gw)
             else:
                 gw.addmm_(dy2.t(), x2)
-            pipe.mark_ready(site.wslot)
             if ctx.has_bias and site.bslot is not None:
                 if not dy2.is_contiguous():
                     dy2 = dy2.contiguous()
-                KERNELS.colsum(dy2, pipe.arena.grad_view(site.bslot), accumulate=not first)
-                pipe.mark_ready(site.bslot)
+                KERNELS.colsum(dy2, pipe.arena.grad_view(site.bslot),
+                               accumulate=not site.bstate.first_touch(pipe.step_id))
+            site.backward_done(pipe)
             return dx, None, None, None
         dw = dy2.t().mm(x2) if ctx.needs_input_grad[1] else None
         db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
@@ -113,20 +111,18 @@ class _ArenaLinearReluFn(torch.autograd.Function):
         y2 = y.reshape(-1, y.shape[-1])
         x2 = x.reshape(-1, x.shape[-1])
         pipe = site.pipeline
-        if pipe is not None and pipe.step_open and dy2.is_cuda:
-            first = site.touched_step != pipe.step_id
-            site.touched_step = pipe.step_id
+        if pipe is not None and pipe.step_open and (dy2.is_cuda or KERNELS is not _native):
             dz = torch.empty_like(dy2)
-            KERNELS.drelu_colsum(dy2, y2, dz, pipe.arena.grad_view(site.bslot), accumulate=not first)
+            KERNELS.drelu_colsum(dy2, y2, dz, pipe.arena.grad_view(site.bslot),
+                                 accumulate=not site.bstate.first_touch(pipe.step_id))
             # dX before any slot is marked ready (the bucket's update overwrites W)
             dx = dz.matmul(weight).view_as(x) if ctx.needs_input_grad[0] else None
             gw = pipe.arena.grad_view(site.wslot)
-            if first:
+            if site.wstate.first_touch(pipe.step_id):
                 torch.mm(dz.t(), x2, out=gw)
             else:
                 gw.addmm_(dz.t(), x2)
-            pipe.mark_ready(site.wslot)
-            pipe.mark_ready(site.bslot)
+            site.backward_done(pipe)
             return dx, None, None, None
         dz = dy2 * (y2 > 0).to(dy2.dtype)
         dx = dz.matmul(weight).view_as(x) if ctx.needs_input_grad[0] else None
@@ -135,24 +131,87 @@ class _ArenaLinearReluFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class SlotState:
+    """Per-PARAMETER bookkeeping shared by every site that uses the parameter (a module applied
+    several times per forward, or weights tied across modules): which step first wrote the
+    gradient slice (store vs. accumulate) and how many backward passes are still to come."""
+    __slots__ = ("touched_step", "fwd_gen", "fwd_count", "bwd_step", "bwd_count")
+
+    def __init__(self) -> None:
+        self.touched_step = -1
+        self.fwd_gen = -1
+        self.fwd_count = 0
+        self.bwd_step = -1
+        self.bwd_count = 0
+
+    def first_touch(self, step_id: int) -> bool:
+        first = self.touched_step != step_id
+        self.touched_step = step_id
+        return first
+
+    def count_forward(self, gen: int) -> None:
+        if self.fwd_gen != gen:
+            self.fwd_gen, self.fwd_count = gen, 0
+        self.fwd_count += 1
+
+    def backward_complete(self, step_id: int, gen: int) -> bool:
+        """One more backward pass through a user of this parameter; True when every forward
+        application counted for this step has been matched (unknown count = complete)."""
+        if self.bwd_step != step_id:
+            self.bwd_step, self.bwd_count = step_id, 0
+        self.bwd_count += 1
+        return self.fwd_gen != gen or self.bwd_count >= self.fwd_count
+
+
 class LinearSite:
-    """Per-module bookkeeping: arena slots of weight/bias and the owning pipeline."""
-    __slots__ = ("module", "wslot", "bslot", "pipeline", "touched_step", "relu")
+    """Per-module bookkeeping: arena slots of weight/bias and the owning pipeline.
+
+    A bucket must not be reduced/updated before the LAST contribution to each of its gradients
+    has been accumulated (stock DDP waits for autograd's AccumulateGrad, which runs once per
+    parameter per backward).  Here gradients are written from inside the layer's backward, so the
+    site counts its applications in the forward pass (training mode, autograd on) and marks its
+    slots ready only when as many backward passes have run; anything left over is marked by
+    ``GradBucketPipeline.finish_step`` (after ``backward()`` returned nothing can be missing)."""
+    __slots__ = ("module", "wslot", "bslot", "pipeline", "relu", "wstate", "bstate")
 
     def __init__(self, module, wslot, bslot, pipeline):
         self.module = module
         self.wslot = wslot
         self.bslot = bslot
         self.pipeline = pipeline
-        self.touched_step = -1
         self.relu = None              # the nn.ReLU this layer absorbed (FRL_B200_FUSE_RELU)
+        states = pipeline.slot_states
+        self.wstate = states.setdefault(wslot.index, SlotState())
+        self.bstate = states.setdefault(bslot.index, SlotState()) if bslot is not None else None
+
+    def count_forward(self) -> None:
+        pipe = self.pipeline
+        if pipe is not None and self.module.training and torch.is_grad_enabled():
+            gen = pipe.forward_gen
+            self.wstate.count_forward(gen)
+            if self.bstate is not None:
+                self.bstate.count_forward(gen)
+
+    def backward_done(self, pipe) -> None:
+        step, gen = pipe.step_id, pipe.forward_gen
+        if self.wstate.backward_complete(step, gen):
+            pipe.mark_ready(self.wslot)
+        else:
+            pipe.defer_ready(self.wslot)
+        if self.bstate is not None:
+            if self.bstate.backward_complete(step, gen):
+                pipe.mark_ready(self.bslot)
+            else:
+                pipe.defer_ready(self.bslot)
 
 
 def _forward(self, x):
+    self._frl_site.count_forward()        # here, not inside the Function: grad mode is off in there
     return _ArenaLinearFn.apply(x, self.weight, self.bias, self._frl_site)
 
 
 def _forward_relu(self, x):
+    self._frl_site.count_forward()
     return _ArenaLinearReluFn.apply(x, self.weight, self.bias, self._frl_site)
 
 
@@ -195,8 +254,10 @@ def patch_linears(model: nn.Module, pipeline) -> List[LinearSite]:
     for mod in model.modules():
         if type(mod) is not nn.Linear or "forward" in mod.__dict__:
             continue
-        if id(mod.weight) not in arena._by_id or not mod.weight.is_cuda:
+        if id(mod.weight) not in arena._by_id:
             continue
+        if not mod.weight.is_cuda and KERNELS is _native:
+            continue                     # the kernels are CUDA-only (CPU tensors: host-logic tests)
         wslot = arena.slot_of(mod.weight)
         bslot = arena.slot_of(mod.bias) if (mod.bias is not None and id(mod.bias) in arena._by_id) else None
         if mod.bias is not None and bslot is None:

@@ -104,6 +104,12 @@ class GradBucketPipeline:
         self._step_open = False
         self.step_id = 0
         self.linear_sites = []
+        # arena_linear bookkeeping: per-parameter touch/application counters, the generation the
+        # forward-application counts belong to (advanced when a step ends) and slots whose layer
+        # ran a backward pass but expects more (module applied several times per forward)
+        self.slot_states = {}
+        self.forward_gen = 0
+        self._deferred = {}
         # timing taps (bench): list of (start_event, end_event, lo, hi) for update launches
         self.record_update_events = False
         self.update_events: List[Tuple[torch.cuda.Event, torch.cuda.Event, int, int]] = []
@@ -113,6 +119,7 @@ class GradBucketPipeline:
         """Call before ``backward()``."""
         self._ready = 0
         self._ready_ids.clear()
+        self._deferred.clear()
         for b in self.buckets:
             b.pending = len(b.slots)
             b.work = None
@@ -145,6 +152,11 @@ class GradBucketPipeline:
         b.pending -= 1
         if b.pending == 0 and (self.distributed or self.eager):
             self._launch_bucket(b)
+
+    def defer_ready(self, slot) -> None:
+        """The slot's gradient was written but more contributions are expected in this backward;
+        ``mark_ready`` follows from the last one, or from ``finish_step`` at the latest."""
+        self._deferred[slot.index] = slot
 
     def _launch_bucket(self, b: _Bucket) -> None:
         """Bucket complete: (all-reduce it and) update it on the side stream, behind everything
@@ -194,6 +206,10 @@ class GradBucketPipeline:
         launches (norm + update of whatever was not updated eagerly) to ``run_tail()``."""
         if not self._step_open:
             raise RuntimeError("finish_step() without begin_step()")
+        for slot in list(self._deferred.values()):    # backward() has returned: nothing is missing
+            self.mark_ready(slot)
+        self._deferred.clear()
+        self.forward_gen += 1
         self._step_open = False
         self._tail_deferred = False
         if self._ready != self._n_slots:

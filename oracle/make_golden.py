@@ -36,6 +36,7 @@ CONFIGS = {
     "toy_adam_amsgrad": ("adam", 0.003, "drop", 2, 0.0, True, "parallel"),
     "toy_rmsprop": ("rmsprop", 0.0005, "drop", 2, 0.0, False, "parallel"),
     "toy_uncertainty": ("sgd", 0.01, "drop", 2, 0.0, False, "uncertainty"),
+    "toy_gradnorm": ("sgd", 0.01, "drop", 2, 0.0, False, "gradnorm"),
 }
 SEED = 0
 BATCH = 64
@@ -125,6 +126,17 @@ def run_oracle(name, cfg):
                                                   crit.log_variance, outputs, targets)
         return ref_loop.train(model, None, None, crit.loss_names, datasets, spec,
                               extra_params=[crit.log_variance], criterion_fn=criterion_fn), problem
+    if kind == "gradnorm":
+        # reference solver_worker.py:551-567: the loop looks up the last shared trunk parameter
+        # on every minibatch and hands it to the criterion before calling it
+        gn = ref_loop.GradNormOracle(list(crit._loss_modules), crit.loss_names, crit._alpha,
+                                     list(crit._base_weights))
+        trunk = list(model.model_base.parameters())
+
+        def criterion_fn(outputs, targets):
+            return gn(outputs, targets, ref_loop.final_shared_param(trunk, outputs))
+        return ref_loop.train(model, None, None, crit.loss_names, datasets, spec,
+                              extra_params=[gn.weight_factors], criterion_fn=criterion_fn), problem
     return ref_loop.train(model, list(crit.loss_modules), list(crit.loss_weights),
                           list(crit.loss_names), datasets, spec), problem
 
@@ -185,10 +197,17 @@ def lr_goldens():
     return out
 
 
-def main():
+def main(only=()):
+    """``python -m oracle.make_golden [config ...]``: regenerate everything, or only the named
+    configurations (their entries are merged into the existing pinning report)."""
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     report = {}
+    report_path = os.path.join(GOLDEN_DIR, "pinning_report.json")
+    if only and os.path.exists(report_path):
+        report = json.load(open(report_path))["configs"]
     for name, cfg in CONFIGS.items():
+        if only and name not in only:
+            continue
         live = run_live_reference(name, cfg)
         trace, problem = run_oracle(name, cfg)
         rows = np.concatenate([trace.losses[k] for k in sorted(
@@ -206,14 +225,15 @@ def main():
                         "max_abs_row_diff": float(np.max(np.abs(rows - live["rows"])))}
         print(name, report[name])
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **live)
-    with open(os.path.join(GOLDEN_DIR, "samplers.json"), "w") as f:
-        json.dump(sampler_goldens(), f)
-    with open(os.path.join(GOLDEN_DIR, "lr_schedules.json"), "w") as f:
-        json.dump(lr_goldens(), f)
-    with open(os.path.join(GOLDEN_DIR, "pinning_report.json"), "w") as f:
+    if not only:
+        with open(os.path.join(GOLDEN_DIR, "samplers.json"), "w") as f:
+            json.dump(sampler_goldens(), f)
+        with open(os.path.join(GOLDEN_DIR, "lr_schedules.json"), "w") as f:
+            json.dump(lr_goldens(), f)
+    with open(report_path, "w") as f:
         json.dump({"torch": torch.__version__, "seed": SEED, "batch": BATCH, "configs": report},
                   f, indent=1)
 
 
 if __name__ == "__main__":
-    main()
+    main(tuple(sys.argv[1:]))

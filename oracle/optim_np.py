@@ -126,3 +126,15 @@ class KernelDouble:
         self.calls.append(("sumsq", n))
         coef, norm = clip_coef(self._np(g), max_norm, pre_scale)
         self._store(out3, [norm * norm, norm, coef])
+
+    # K6 / K6b stand-ins (bias gradient of a linear layer written into the arena)
+    def colsum(self, x, out, accumulate=False):
+        self.calls.append(("colsum", x.shape[1]))
+        tot = x.detach().float().sum(0)
+        out.copy_((out.float() + tot if accumulate else tot).to(out.dtype))
+
+    def drelu_colsum(self, dy, act, dz, out, accumulate=False):
+        self.calls.append(("drelu_colsum", dy.shape[1]))
+        dz.copy_(dy * (act > 0).to(dy.dtype))
+        tot = dz.float().sum(0)
+        out.copy_((out.float() + tot if accumulate else tot).to(out.dtype))

@@ -7,6 +7,8 @@ reference line by line, exactly the part of the reference the B200 path replaces
     create_lr_scheduler + get_lr solver.py:191-218, lr_scheduler.py:29-33, 65-78 -> lr_at_epoch
     ParallelCriterion.forward    criteria.py:42-61      -> parallel_criterion
     UncertaintyWeightedCriterion criteria.py:108-148    -> uncertainty_criterion
+    GradNormWeightedCriterion    criteria.py:151-260    -> GradNormOracle
+    MultiTaskModel.final_shared_params  model.py:32-50  -> final_shared_param
     MaskedLoss.forward           criteria.py:272-287    -> masked_loss
     SolverWorker._pass_one_epoch / _pass_one_minibatch   solver_worker.py:412-594 -> train
     ScaffoldSampler.__iter__ / per_node_randperm         sampler.py:17-87 -> rank_indices
@@ -166,6 +168,55 @@ def uncertainty_criterion(loss_modules, kinds, names, log_variance, outputs, tar
             split[name] = 1.0 / torch.exp(log_variance[i]) * raw
         costs.append(0.5 * log_variance[i])
     return sum(split.values()) + sum(costs), split
+
+
+def final_shared_param(trunk_params: Sequence[nn.Parameter], outputs: Sequence[torch.Tensor]):
+    """reference model.py:32-50: breadth-first walk from the FIRST head's grad_fn; the first
+    AccumulateGrad node whose variable is a trunk parameter."""
+    from queue import Queue
+    todo = Queue()
+    todo.put(outputs[0].grad_fn)
+    while not todo.empty():
+        fn = todo.get()
+        for nxt, _ in fn.next_functions:
+            if hasattr(nxt, "variable") and any(nxt.variable is p for p in trunk_params):
+                return nxt.variable
+            if nxt is not None:
+                todo.put(nxt)
+    raise RuntimeError("Unable to find any shared parameters in the model")
+
+
+class GradNormOracle:
+    """reference criteria.py:151-260, stated as a plain object: ``weight_factors`` is the
+    trainable T-vector (zeros), the baseline losses are captured by the first call."""
+
+    def __init__(self, loss_modules, names, alpha: float, base_weights=None) -> None:
+        self.loss_modules, self.names, self.alpha = list(loss_modules), list(names), alpha
+        self.T = len(self.loss_modules)
+        self.weight_factors = nn.Parameter(torch.zeros(self.T))
+        self.base_weights = base_weights or [1] * self.T
+        self.baseline: Optional[List[float]] = None
+
+    def __call__(self, outputs, targets, shared_param):
+        T = self.T
+        task = [self.base_weights[i] * self.loss_modules[i](outputs[i], *targets[i])      # :183-186
+                for i in range(T)]
+        if self.baseline is None:                                                         # :188-189
+            self.baseline = [l.item() for l in task]
+        inv = [task[i] / self.baseline[i] for i in range(T)]                              # :193-196
+        mean_inv = sum(inv) / len(inv)
+        rel = [r / mean_inv for r in inv]                                                 # :198-201
+        dl = [g.detach() for g in torch.autograd.grad(task, outputs, retain_graph=True)]  # :207-212
+        weights = self.weight_factors.softmax(0) * T                                      # :219
+        norms = [torch.autograd.grad(outputs[i], shared_param, weights[i] * dl[i],        # :224-234
+                                     retain_graph=True, create_graph=True)[0].norm()
+                 for i in range(T)]
+        mean_norm = sum(norms) / len(norms)                                               # :239
+        wanted = [mean_norm * (r ** self.alpha) for r in rel]                             # :240-243
+        grad_loss = sum(torch.nn.functional.l1_loss(n, w.detach())                        # :244-248
+                        for n, w in zip(norms, wanted))
+        weighted = [weights[i].detach() * task[i] for i in range(T)]                      # :253-256
+        return sum(weighted) + grad_loss, dict(zip(self.names, task))                     # :258-260
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,163 @@
+"""Parity of the HEADLINE configuration (BASELINE.json configs[1]: 2-task MLP, 4096-d input,
+3x[Linear(4096,4096)+ReLU] trunk, heads 4096->1000 CE + 4096->64 MSE, 54 703 144 parameters)
+against the CPU oracle, at a batch the oracle affords (256).
+
+Both sides build the model from the same seed and train on the same batches; the B200 side goes
+through ``Solver.build_worker`` + ``SolverWorker._pass_one_minibatch`` — the call ``bench.py``
+times — with every switch of the benchmarked configuration: arena-born Linear gradients,
+fused Linear+ReLU units, fused criterion, fused update, CUDA-graph replay on and off.
+
+Bounds (BASELINE.json north_star): fp32 losses 1e-5 rel; fp32 first-step gradients 1e-5 of each
+tensor's largest entry (a 4096-term fp32 dot product summed in another order cannot agree to
+1e-5 of an entry that cancels to ~0); bf16 mode losses 1e-2 rel and gradients 1e-2 relative L2.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+import frl_b200  # noqa: F401
+from frl_b200 import synthetic
+from frl_b200.solver import Solver, SolverWorkerArgs
+from frl_b200.types import Device, Precision
+from oracle import ref_loop
+
+pytestmark = pytest.mark.gpu
+
+WIDTH, N_CLASSES, REG_DIM, DEPTH, BATCH, STEPS = 4096, 1000, 64, 3, 256, 6
+LR = {"sgd": 0.01, "adam": 1e-3}
+
+
+def _batches():
+    g = torch.Generator().manual_seed(1234)
+    return [(torch.randn(BATCH, WIDTH, generator=g), torch.randint(0, N_CLASSES, (BATCH,), generator=g),
+             torch.randn(BATCH, REG_DIM, generator=g)) for _ in range(STEPS)]
+
+
+_ORACLE = {}
+
+
+def _oracle(algo):
+    """CPU reference: stock fp32 torch + torch.optim via oracle/ref_loop (cached per algorithm)."""
+    if algo in _ORACLE:
+        return _ORACLE[algo]
+    ns = synthetic.api_namespace("frl_b200")
+    torch.manual_seed(0)
+    problem = synthetic.make_mlp_problem(ns, "/tmp/unused", n_train=8, width=WIDTH,
+                                         n_classes=N_CLASSES, reg_dim=REG_DIM, depth=DEPTH)
+    model, crit = problem.get_model(), problem.get_criterion()
+    mods, weights, names = list(crit.loss_modules), list(crit.loss_weights), list(crit.loss_names)
+    params = list(model.parameters())
+    opt = ref_loop.make_optimizer(params, ref_loop.OptimSpec(algo=algo, lr=LR[algo]))
+    model.train()
+    rows, first_grads = [], None
+    for x, y, r in _batches():
+        _, total, sub = ref_loop.reference_minibatch(
+            model, lambda o, t: ref_loop.parallel_criterion(mods, weights, names, o, t), opt, params,
+            0.0, [x], [(y,), (r,)])
+        rows.append([total.item()] + [sub[n].item() for n in names])
+        if first_grads is None:
+            first_grads = [p.grad.detach().clone() for p in params]
+    _ORACLE[algo] = (np.asarray(rows, dtype=np.float64), first_grads,
+                     [p.detach().clone() for p in params])
+    return _ORACLE[algo]
+
+
+def _b200(algo, precision, graph, monkeypatch):
+    monkeypatch.setenv("FRL_B200_CUDA_GRAPH", graph)
+    ns = synthetic.api_namespace("frl_b200")
+    t = ns.types
+    save_dir = tempfile.mkdtemp(prefix="frl_b200_mlp_")
+    torch.manual_seed(0)
+    problem = synthetic.make_mlp_problem(ns, save_dir, n_train=8, width=WIDTH, n_classes=N_CLASSES,
+                                         reg_dim=REG_DIM, depth=DEPTH)
+    run_opts = t.RunOpts(optim=t.OptimOpts(algo=t.OptAlgorithm(algo), lr=LR[algo]), batchSize=BATCH,
+                         nEpochs=1, numThreads=0, singleThreaded=True, numVisualizedSamples=0)
+    args = SolverWorkerArgs(run_opts=run_opts, problem=problem, save_dir=save_dir,
+                            run_device=Device.GPU, node_idx=0, node_count=1, rank=0, local_rank=0,
+                            world_size=1, group_name=None, init_method="", precision=precision)
+    worker, _, _ = Solver.build_worker(args)
+    worker.model.train()
+    worker.criterion.train()
+    assert worker.arena.n_trainable == 54_703_144
+    assert len(worker.pipeline.linear_sites) == 5
+    assert sum(s.relu is not None for s in worker.pipeline.linear_sites) == 3
+    rows, first_grads = [], None
+    for i, (x, y, r) in enumerate(_batches()):
+        _, total, sub, _ = worker._pass_one_minibatch(
+            i, t.Split.TRAIN, [x.cuda()], [(y.cuda(),), (r.cuda(),)])
+        rows.append([float(total)] + [float(sub[n]) for n in worker.criterion.loss_names])
+        if first_grads is None:
+            torch.cuda.synchronize()
+            first_grads = [worker.arena.grad_view(s).float().cpu().clone()
+                           for s in worker.arena.slots if s.is_model]
+    torch.cuda.synchronize()
+    if graph == "1":
+        assert worker.graphed is not None and len(worker.graphed._graphs) == 1   # steps 4.. replayed
+    final = [worker.arena.master_view(s).cpu().clone() for s in worker.arena.slots if s.is_model]
+    return np.asarray(rows, dtype=np.float64), first_grads, final
+
+
+@pytest.mark.parametrize("graph", ["0", "1"])
+@pytest.mark.parametrize("algo", ["sgd", "adam"])
+def test_mlp_config_matches_oracle_fp32(algo, graph, monkeypatch):
+    want_rows, want_grads, want_final = _oracle(algo)
+    rows, grads, final = _b200(algo, Precision.FP32, graph, monkeypatch)
+    np.testing.assert_allclose(rows, want_rows, rtol=1e-5, atol=0)
+    for g, w in zip(grads, want_grads):
+        scale = float(w.abs().max())
+        assert float((g - w).abs().max()) <= 1e-5 * scale, (tuple(w.shape), float((g - w).abs().max()) / scale)
+    # six steps of weights: SGD moves by lr*g (1e-5 of the largest gradient entry again);
+    # Adam's m/(sqrt(v)+eps) turns a last-bit gradient difference into a visible fraction of lr
+    # where v is tiny (final weights are outside the 1e-5 claim)
+    for a, b in zip(final, want_final):
+        tol = 1e-6 if algo == "sgd" else 5e-5
+        assert float((a - b).abs().max()) <= tol, (tuple(b.shape), float((a - b).abs().max()))
+
+
+@pytest.mark.parametrize("graph", ["0", "1"])
+@pytest.mark.parametrize("algo", ["sgd", "adam"])
+def test_mlp_config_matches_oracle_bf16(algo, graph, monkeypatch):
+    """The benchmarked precision: bf16 forward/backward/gradients, fp32 master + state."""
+    want_rows, want_grads, _ = _oracle(algo)
+    rows, grads, _ = _b200(algo, Precision.BF16, graph, monkeypatch)
+    np.testing.assert_allclose(rows, want_rows, rtol=1e-2, atol=0)
+    worst = 0.0
+    for g, w in zip(grads, want_grads):
+        worst = max(worst, float((g - w).norm() / w.norm()))
+    print("bf16 first-step gradients: worst relative L2 error %.3e" % worst)
+    assert worst <= 1e-2
+
+
+def test_reused_linear_on_the_device_with_eager_bucket_updates(monkeypatch):
+    """ADVICE r1 (high) on the real kernels: a Linear applied twice per forward, per-bucket eager
+    updates on the side stream (the multi-GPU launch pattern, forced on one GPU): the bucket must
+    wait for the second backward pass.  Compared with stock torch SGD on the same device."""
+    from frl_b200 import fused_optim, grad_sync
+    from frl_b200.arena import ParamArena
+    from frl_b200.types import OptAlgorithm, OptimOpts
+    from test_host_logic import _Reuse
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    net, ref = _Reuse(3).to(dev), _Reuse(3).to(dev)
+    arena = ParamArena(net.parameters(), device=dev)
+    opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm.SGD, lr=0.05))
+    pipe = grad_sync.GradBucketPipeline(arena, opt, world_size=1, bucket_cap_mb=0.0001,
+                                        eager_update=True)
+    assert pipe.eager and len(pipe.buckets) > 2 and pipe.patch_linears(net) == 4
+    ref_opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-5)
+    g = torch.Generator().manual_seed(5)
+    for _ in range(4):
+        x = torch.randn(16, 7, generator=g).to(dev)
+        out = net(x)
+        pipe.begin_step()
+        out.square().mean().backward()
+        pipe.finish_step()
+        ref_opt.zero_grad()
+        ref(x).square().mean().backward()
+        ref_opt.step()
+    torch.cuda.synchronize()
+    for a, b in zip(net.parameters(), ref.parameters()):
+        torch.testing.assert_close(a.detach(), b.detach(), rtol=2e-5, atol=2e-7)

@@ -358,3 +358,81 @@ def test_watchdog_kicks_postpone_the_deadline_and_a_stall_fires_it():
             for _ in range(300):                            # a "hung minibatch": no kick for > 200 ms
                 time.sleep(0.01)
     assert dog.fired
+
+
+# ---- a Linear applied twice per forward (weight reuse) under the eager per-bucket pipeline --------
+
+class _Reuse(nn.Module):
+    """`shared` runs twice per forward and `tied` borrows `first`'s weight: both parameters get
+    two gradient contributions per backward."""
+
+    def __init__(self, seed):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.first = nn.Linear(7, 7)
+        self.shared = nn.Sequential(nn.Linear(7, 7), nn.ReLU())
+        self.tied = nn.Linear(7, 7)
+        self.tied.weight = self.first.weight
+        self.head = nn.Linear(7, 2)
+
+    def forward(self, x):
+        h = torch.relu(self.first(x))
+        h = self.shared(self.shared(h))
+        return self.head(torch.relu(self.tied(h)))
+
+
+def _reuse_rank_main(rank, world, port, patched, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from frl_b200 import arena_linear
+    d = KernelDouble()
+    fused_optim.KERNELS = d
+    grad_sync.KERNELS = d
+    arena_linear.KERNELS = d
+    net = _Reuse(3)
+    arena = ParamArena(net.parameters(), device="cpu")
+    opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm.SGD, lr=0.05))
+    pipe = grad_sync.GradBucketPipeline(arena, opt, world_size=world, bucket_cap_mb=0.0001,
+                                        first_bucket_mb=0.00005, eager_update=True)
+    assert pipe.eager and len(pipe.buckets) > 2
+    if patched:
+        assert pipe.patch_linears(net) == 4
+        assert sum(s.relu is not None for s in pipe.linear_sites) == 1
+    pipe.broadcast_parameters(src=0)
+    g = torch.Generator().manual_seed(5)
+    net.train()
+    for step in range(3):
+        x = torch.randn(8 * world, 7, generator=g)
+        if step == 1:                       # a forward that is never back-propagated (eval split)
+            net.eval()
+            net(x[rank::world])
+            net.train()
+        out = net(x[rank::world])
+        pipe.begin_step()
+        out.square().mean().backward()
+        pipe.finish_step()
+    torch.save([p.detach().clone() for p in net.parameters()], os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("patched", [True, False])
+def test_reused_and_tied_linears_wait_for_their_last_gradient(tmp_path, patched):
+    """with gradients written from inside the layer's backward, a bucket must
+    not be reduced/updated after the FIRST of several backward passes through a reused Linear."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_reuse_rank_main, args=(world, port, patched, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
+    for a, b in zip(r0, r1):
+        assert torch.equal(a, b)
+    ref = _Reuse(3)
+    ref_opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-5)
+    g = torch.Generator().manual_seed(5)
+    for step in range(3):
+        x = torch.randn(8 * world, 7, generator=g)
+        ref_opt.zero_grad()
+        ref(x).square().mean().backward()
+        ref_opt.step()
+    for a, b in zip(r0, ref.parameters()):
+        np.testing.assert_allclose(a.numpy(), b.detach().numpy(), rtol=2e-5, atol=2e-7)
