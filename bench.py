@@ -4,6 +4,10 @@ MLP Problem (BASELINE.json configs[1] at N=1, configs[2] at N>1; batch 4096 per 
 
     python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
     python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host CPU
+    python bench.py --impl torch-gpu --gpus N ...            # stock PyTorch on the GPU: autocast +
+                                                             # torch.optim (+ DDP at N>1), the
+                                                             # "kernel to beat" of SURVEY §8(d)
+    python bench.py --workload resnet18|resnet50x4 ...       # BASELINE configs[3] / configs[4]
 
 One JSON line on stdout (rank 0).  Everything else goes to stderr.
 """
@@ -32,35 +36,90 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--algo", default="sgd", choices=["sgd", "adam", "rmsprop"])
-    ap.add_argument("--batch", type=int, default=4096, help="samples per rank per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch-gpu"])
+    ap.add_argument("--workload", default="mlp", choices=sorted(WORKLOADS))
+    ap.add_argument("--algo", default=None, choices=["sgd", "adam", "rmsprop"],
+                    help="default: the workload's (mlp/resnet18 sgd, resnet50x4 adam)")
+    ap.add_argument("--batch", type=int, default=None, help="samples per rank per step (mlp 4096, resnets 256)")
+    ap.add_argument("--image", type=int, default=224, help="resnet workloads: image side")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-batch", type=int, default=1024, help="CPU arm: samples per step (bounded sample)")
+    ap.add_argument("--cpu-batch", type=int, default=None,
+                    help="CPU arm: samples per step (default: the workload's batch for --impl reference, "
+                         "a bounded sample — mlp 1024, resnets 32 — for the in-line cpu_baseline leg)")
+    ap.add_argument("--torch-optim", default="default", choices=["default", "fused"],
+                    help="torch-gpu arm: torch.optim as the reference builds it (foreach) or fused=True")
+    ap.add_argument("--no-torch-baseline", action="store_true",
+                    help="b200 arm: skip the in-process stock-PyTorch-GPU comparison")
+    ap.add_argument("--no-parity-check", action="store_true",
+                    help="b200 arm, N>1: skip the K7-vs-NCCL self-check after the timed region")
     ap.add_argument("--cpu-steps", type=int, default=3, help="cpu_baseline leg: timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=None, help="gradient bucket cap (MiB)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph (1) or issue it eagerly (0)")
     ap.add_argument("--profile", default=None, help="write a torch.profiler chrome trace of 5 steps here")
-    return ap.parse_args()
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.algo is None:
+        args.algo = wl["algo"]
+    if args.batch is None:
+        args.batch = wl["batch"]
+    return args
 
 
 # --------------------------------------------------------------------------------------------------
 # shared: the Problem
 # --------------------------------------------------------------------------------------------------
 
-def workload_name(batch, algo):
-    return ("2-task MLP Problem: 4096-d in, 3x[Linear(4096,4096)+ReLU] trunk, heads 4096->1000 CE + "
-            "4096->64 MSE (54.70M params), batch %d/rank, %s wd=1e-5" % (
-                batch, {"sgd": "SGD momentum 0.9 lr 0.01", "adam": "Adam lr 1e-3",
-                        "rmsprop": "RMSprop momentum 0.9 lr 1e-3"}[algo]))
+WORKLOADS = {
+    # BASELINE.json configs[1]/[2] (the metric's configuration), configs[3], configs[4]
+    "mlp": {"algo": "sgd", "batch": 4096, "cpu_sample_batch": 1024, "params": 54_703_144,
+            "what": "2-task MLP Problem: 4096-d in, 3x[Linear(4096,4096)+ReLU] trunk, heads 4096->1000 CE + "
+                    "4096->64 MSE (54.70M params)"},
+    "resnet18": {"algo": "sgd", "batch": 256, "cpu_sample_batch": 32, "params": 11_689_512,
+                 "what": "single-task ResNet-18 Problem: torchvision resnet18 trunk + Linear(512,1000) CE head "
+                         "(11.69M params, 62 tensors), synthetic 3x%dx%d images"},
+    "resnet50x4": {"algo": "adam", "batch": 256, "cpu_sample_batch": 16, "params": 25_790_618,
+                   "what": "4-task Problem over a shared ResNet-50 trunk: heads 2048->{1000 CE, 100 CE, 10 MSE, "
+                           "4 MSE} (25.79M params, 167 tensors), synthetic 3x%dx%d images"},
+}
+ALGO_TEXT = {"sgd": "SGD momentum 0.9 lr 0.01", "adam": "Adam lr 1e-3 (L2-coupled, as the reference)",
+             "rmsprop": "RMSprop momentum 0.9 lr 1e-3"}
 
 
-def build_problem(ns, save_dir):
+def workload_name(args, batch=None):
+    what = WORKLOADS[args.workload]["what"]
+    if "%d" in what:
+        what = what % (args.image, args.image)
+    return "%s, batch %d/rank, %s wd=1e-5" % (what, batch or args.batch, ALGO_TEXT[args.algo])
+
+
+def build_problem(ns, save_dir, args, n_train=64, pinned=False, fast_fields=False, uint8=False):
     from frl_b200 import synthetic
-    return synthetic.make_mlp_problem(ns, save_dir, n_train=64, width=WIDTH, n_classes=N_CLASSES,
-                                      reg_dim=REG_DIM, depth=DEPTH)
+    if args.workload == "mlp":
+        return synthetic.make_mlp_problem(ns, save_dir, n_train=n_train, width=WIDTH, n_classes=N_CLASSES,
+                                          reg_dim=REG_DIM, depth=DEPTH, pinned=pinned, fast_fields=fast_fields)
+    return synthetic.make_resnet_problem(ns, save_dir, args.workload, image=args.image, n_train=n_train,
+                                         pinned=pinned, uint8=uint8)
+
+
+def synthetic_batch(args, batch, gen, device):
+    """One (data, target) minibatch of the workload's shape, generated on ``device``."""
+    import torch
+    from frl_b200 import synthetic
+    if args.workload == "mlp":
+        x = torch.randn(batch, WIDTH, device=device, generator=gen)
+        y = torch.randint(0, N_CLASSES, (batch,), device=device, generator=gen)
+        r = torch.randn(batch, REG_DIM, device=device, generator=gen)
+        return [x], [(y,), (r,)]
+    x = torch.randn(batch, 3, args.image, args.image, device=device, generator=gen)
+    target = []
+    for kind, dim, _, _ in synthetic.RESNET_CONFIGS[args.workload][1]:
+        if kind == "cls":
+            target.append((torch.randint(0, dim, (batch,), device=device, generator=gen),))
+        else:
+            target.append((torch.randn(batch, dim, device=device, generator=gen),))
+    return [x], target
 
 
 def run_opts_for(ns, algo, batch):
@@ -71,67 +130,106 @@ def run_opts_for(ns, algo, batch):
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle restatement) on the host cores
+# CPU arm: the reference itself (oracle/_ref) or its restatement (oracle/ref_loop) on the host cores
 # --------------------------------------------------------------------------------------------------
 
-def time_cpu_reference(algo, batch, steps, warmup):
-    """Reference `_pass_one_minibatch` (oracle/ref_loop.reference_minibatch: stock fp32 torch on
-    the CPU, torch.optim, un-fused criterion) on a bounded sample of the workload."""
+def time_cpu_reference(args, batch, steps, warmup):
+    """The reference's `_pass_one_minibatch` on the host cores, on a bounded sample of the workload.
+
+    kind "reference": the UNMODIFIED reference (packed by oracle/build_ref.py into oracle/_ref,
+    imported as frldistml.scaffold) — its own SolverWorker, criteria and `_create_optimizer` on
+    the synthetic Problem instantiated against ITS plugin API, `cpuonly`;
+    kind "port": oracle/ref_loop.reference_minibatch (the restatement) when oracle/_ref is absent."""
     import torch
     import frl_b200  # noqa: F401  (only the synthetic Problem definition)
     from frl_b200 import synthetic
-    from oracle import ref_loop
     # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 by default)
     try:
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except AttributeError:
         torch.set_num_threads(os.cpu_count() or 1)
-    ns = synthetic.api_namespace("frl_b200")
-    torch.manual_seed(0)
-    problem = build_problem(ns, "/tmp/frl_b200_bench_cpu")
-    model = problem.get_model()
-    crit = problem.get_criterion()
-    mods, weights, names = list(crit.loss_modules), list(crit.loss_weights), list(crit.loss_names)
-    spec = ref_loop.OptimSpec(algo=algo, lr=0.01 if algo == "sgd" else 1e-3)
-    params = list(model.parameters())
-    opt = ref_loop.make_optimizer(params, spec)
-
-    def criterion_fn(outputs, targets):
-        return ref_loop.parallel_criterion(mods, weights, names, outputs, targets)
-
+    from oracle import ref_shim
     g = torch.Generator().manual_seed(1234)
-    x = torch.randn(batch, WIDTH, generator=g)
-    y = torch.randint(0, N_CLASSES, (batch,), generator=g)
-    r = torch.randn(batch, REG_DIM, generator=g)
-    model.train()
+    data, target = synthetic_batch(args, batch, g, torch.device("cpu"))
+    lr = 0.01 if args.algo == "sgd" else 1e-3
+    if ref_shim.reference_available():
+        ref_shim.import_reference()
+        ns = synthetic.api_namespace("frldistml.scaffold")
+        from frldistml.scaffold import solver as ref_solver
+        from frldistml.scaffold import solver_worker as ref_sw
+        t = ns.types
+        torch.manual_seed(0)
+        problem = build_problem(ns, "/tmp/frl_b200_bench_cpu", args)
+        model, crit = problem.get_model(), problem.get_criterion()
+        run_opts = t.RunOpts(optim=t.OptimOpts(algo=t.OptAlgorithm(args.algo), lr=lr), batchSize=batch,
+                             nEpochs=1, numThreads=0, singleThreaded=True, cpuonly=True,
+                             numVisualizedSamples=0)
+        from itertools import chain
+        opt = ref_solver._create_optimizer(chain(model.parameters(), crit.parameters()), run_opts.optim)
+        # the dataset cache is an out-of-scope subsystem the minibatch never touches: hand the
+        # constructor the one attribute it checks instead of 85 % of the host's RAM
+        from types import SimpleNamespace
+        worker = ref_sw.SolverWorker(model, crit, opt, torch.device("cpu"), run_opts,
+                                     SimpleNamespace(local_worker_count=1),
+                                     local_rank=0, node_idx=0, node_count=1)
+        model.train()
+        crit.train()
+
+        def step(i):
+            worker._pass_one_minibatch(i, t.Split.TRAIN, data, target)
+
+        kind = "reference"
+        how = ("the unmodified reference's SolverWorker._pass_one_minibatch (oracle/_ref, torch %s CPU ops + "
+               "torch.optim)" % torch.__version__)
+    else:
+        from oracle import ref_loop
+        ns = synthetic.api_namespace("frl_b200")
+        torch.manual_seed(0)
+        problem = build_problem(ns, "/tmp/frl_b200_bench_cpu", args)
+        model, crit = problem.get_model(), problem.get_criterion()
+        mods, weights, names = list(crit.loss_modules), list(crit.loss_weights), list(crit.loss_names)
+        params = list(model.parameters())
+        opt = ref_loop.make_optimizer(params, ref_loop.OptimSpec(algo=args.algo, lr=lr))
+        model.train()
+
+        def step(i):
+            ref_loop.reference_minibatch(
+                model, lambda o, tg: ref_loop.parallel_criterion(mods, weights, names, o, tg), opt, params,
+                0.0, data, target)
+
+        kind = "port"
+        how = "oracle/ref_loop.reference_minibatch (stock torch CPU ops + torch.optim)"
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        ref_loop.reference_minibatch(model, criterion_fn, opt, params, 0.0, [x], [(y,), (r,)])
+        step(i)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     total = sum(times)
     return {"value": batch * steps / total, "unit": "samples/s", "cores": torch.get_num_threads(),
-            "host_cpus": os.cpu_count(), "kind": "port",
-            "sample": "%d timed steps (+%d warm-up) of the same 2-task MLP at batch %d, fp32, "
-                      "oracle/ref_loop.reference_minibatch (stock torch CPU ops + torch.optim)" % (
-                          steps, warmup, batch),
+            "host_cpus": os.cpu_count(), "kind": kind, "batch": batch,
+            "sample": "%d timed steps (+%d warm-up) of the same workload at batch %d, fp32, %s" % (
+                steps, warmup, batch, how),
             "ms_per_step": 1e3 * total / steps, "step_p50_ms": 1e3 * statistics.median(times)}
 
 
 def main_reference(args, rank):
     if rank != 0:
         return
-    res = time_cpu_reference(args.algo, args.cpu_batch, args.steps, args.warmup)
+    # the driver's reference arm runs the metric's own configuration (same batch as the b200 arm)
+    # unless a smaller bounded sample is asked for
+    batch = args.cpu_batch or args.batch
+    res = time_cpu_reference(args, batch, args.steps, args.warmup)
+    note = "reference implementation on the host CPU, fp32"
+    if batch != args.batch:
+        note += "; bounded sample: batch %d per step instead of %d" % (batch, args.batch)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": res["ms_per_step"], "step_p50_ms": res["step_p50_ms"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.cpu_batch, args.algo),
-                       "note": "reference algorithm on the host CPU; bounded sample: batch %d "
-                               "per step instead of %d" % (args.cpu_batch, args.batch)},
+            "config": {"workload": workload_name(args, batch), "note": note},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
@@ -192,6 +290,164 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
+# stock-PyTorch-GPU arm: what the reference does on a GPU (SURVEY §8d "kernel to beat")
+# --------------------------------------------------------------------------------------------------
+
+def run_torch_gpu(args, rank, local_rank, world, steps, warmup, with_e2e=True, profile_path=None):
+    """The reference's GPU training step with stock PyTorch only (reference solver.py:162-188
+    `_create_optimizer` = torch.optim defaults, :265-294 DistributedDataParallel(device_ids=[rank])
+    at world > 1; solver_worker.py:551-592 forward / criterion / isnan / zero_grad / backward /
+    step) on the same Problem, batch and synthetic data as the b200 arm.  `--precision bf16` runs
+    the forward under torch.autocast(bfloat16) with fp32 parameters and optimizer state — the same
+    numerical recipe as this repo's BF16 mode; fp32 is the reference's literal configuration.
+    Nothing of this repo's kernels, arena or pipeline is on this path (only the synthetic Problem
+    definition, instantiated on the package's plugin API)."""
+    import torch
+    import torch.distributed as dist
+    import frl_b200  # noqa: F401
+    from frl_b200 import synthetic
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    ns = synthetic.api_namespace("frl_b200")
+    B = args.batch
+    torch.manual_seed(0)
+    problem = build_problem(ns, "/tmp/frl_b200_bench_torch_%d" % rank, args)
+    model = problem.get_model().to(dev)
+    crit = problem.get_criterion()
+    mods = [m.to(dev) for m in crit.loss_modules]
+    weights, names = list(crit.loss_weights), list(crit.loss_names)
+    lr = 0.01 if args.algo == "sgd" else 1e-3
+    kw = {"fused": True} if args.torch_optim == "fused" else {}
+    params = list(model.parameters())
+    if args.algo == "sgd":
+        opt = torch.optim.SGD(params, lr=lr, momentum=0.9, weight_decay=1e-5, **kw)
+    elif args.algo == "adam":
+        opt = torch.optim.Adam(params, lr=lr, weight_decay=1e-5, eps=1e-8, **kw)
+    else:
+        opt = torch.optim.RMSprop(params, lr=lr, momentum=0.9, weight_decay=1e-5)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
+    autocast = args.precision == "bf16"
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool = [synthetic_batch(args, B, gen, dev) for _ in range(4)]
+    net.train()
+
+    def step(data, target):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out = net(data)
+        split = {n: w * m(o.float(), *t) for n, w, m, o, t in zip(names, weights, mods, out, target)}
+        total = sum(split.values())
+        if torch.isnan(total).any():                 # the reference's per-step host sync (:569)
+            raise FloatingPointError("Losses become NaN")
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        tv = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        return tv.item()
+
+    for i in range(warmup):
+        step(*pool[i % 4])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(*pool[i % 4])
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    res = {"value": world * B / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms,
+           "optimizer": "torch.optim.%s(%s)" % (type(opt).__name__, "fused=True" if kw else "defaults: foreach"),
+           "grad_sync": "DistributedDataParallel + NCCL" if world > 1 else "none (1 GPU)",
+           "precision": "torch.autocast(bfloat16) forward, fp32 parameters/gradients/state" if autocast else "fp32",
+           "step": "eager launches incl. the reference's isnan host sync"}
+    if profile_path and rank == 0 or (profile_path and world > 1):
+        from contextlib import nullcontext
+        from torch.profiler import ProfilerActivity, profile
+        ctx = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) if rank == 0 else nullcontext()
+        with ctx as prof:
+            for i in range(5):
+                step(*pool[i % 4])
+            torch.cuda.synchronize()
+        if rank == 0:
+            rows = sorted(((e.key, e.device_time_total / 5.0, e.count / 5.0) for e in prof.key_averages()
+                           if e.device_time_total > 0), key=lambda r: -r[1])
+            with open(profile_path, "w") as f:
+                json.dump({"impl": "torch-gpu", "ms_per_step": ms, "kernels_us_per_step":
+                           [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:40]]},
+                          f, indent=1)
+        barrier()
+    if with_e2e:
+        # end to end, the way the reference feeds a GPU: this step's batch comes from host memory
+        # (pinned here — the reference's is pageable) and the loss is read back every step
+        host = [([t.cpu().pin_memory() for t in d], [tuple(t.cpu().pin_memory() for t in h) for h in tg])
+                for d, tg in pool]
+
+        def e2e_step(i):
+            d, tg = host[i % 4]
+            data = [t.to(dev, non_blocking=True) for t in d]
+            target = [tuple(t.to(dev, non_blocking=True) for t in h) for h in tg]
+            return step(data, target).item()
+
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            e2e_step(i)
+        e1.record()
+        barrier()
+        ems = max_over_ranks(e0.elapsed_time(e1)) / steps
+        h2d = sum(t.numel() * t.element_size() for t in host[0][0]) + sum(
+            t.numel() * t.element_size() for h in host[0][1] for t in h)
+        res["e2e"] = {"value": world * B / (ems / 1e3), "unit": "samples/s", "ms_per_step": ems,
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+    del net, model, opt, pool
+    torch.cuda.empty_cache()
+    return res
+
+
+def main_torch_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    with ClockSampler(local_rank) as clocks:
+        res = run_torch_gpu(args, rank, local_rank, world, args.steps, args.warmup, with_e2e=not args.no_e2e,
+                            profile_path=args.profile)
+    if rank == 0:
+        line = {"impl": "torch-gpu", "metric": METRIC, "value": res["value"], "unit": "samples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args), "global_batch": args.batch * world,
+                           "parallelism": "dp%d" % world, "optimizer": res["optimizer"],
+                           "grad_allreduce": res["grad_sync"], "precision": res["precision"],
+                           "step_issue": res["step"]},
+                "e2e": res.get("e2e"), "gpu_launches": 0, "clocks": clocks.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
+
+
+# --------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------
 
@@ -199,6 +455,125 @@ BYTES_PER_PARAM = {  # algorithmic, fp32 master + state, bf16 gradient read, bf1
     ("sgd", "bf16"): 2 + 4 + 4 + 4 + 4 + 2, ("sgd", "fp32"): 4 + 4 + 4 + 4 + 4,
     ("adam", "bf16"): 2 + 4 * 3 + 4 * 3 + 2, ("adam", "fp32"): 4 * 4 + 4 * 3,
     ("rmsprop", "bf16"): 2 + 4 * 3 + 4 * 3 + 2, ("rmsprop", "fp32"): 4 * 4 + 4 * 3}
+
+
+def shared_global_fields(sample_fields, n_rows, rank, dev, bf16_fields=()):
+    """world > 1: one copy of the synthetic dataset for the whole box.  Rank 0 writes every field
+    as a file in /dev/shm (a base block of random rows tiled to ``n_rows``: the values are
+    synthetic, the row count and byte volume are what the loop sees), every rank maps the files and
+    page-locks the mapping (cudaHostRegister) so its GPU can read the rows in place."""
+    import torch
+    import torch.distributed as dist
+    tag = os.environ.get("MASTER_PORT", "0")
+    out = {}
+    paths = {name: "/dev/shm/frl_b200_bench_%s_%s.bin" % (tag, name) for name in sample_fields}
+    # fields the transform declares bf16-tolerant are stored in that wire dtype (what the loader
+    # would otherwise make of them once per rank: world copies of the global array)
+    sample_fields = {k: (v.to(torch.bfloat16) if k in bf16_fields and v.dtype == torch.float32 else v)
+                     for k, v in sample_fields.items()}
+    if rank == 0:
+        g = torch.Generator().manual_seed(7)
+        for name, sample in sample_fields.items():
+            shape = (n_rows,) + tuple(sample.shape[1:])
+            t = torch.from_file(paths[name], shared=True, size=int(torch.tensor(shape).prod()),
+                                dtype=sample.dtype).view(shape)
+            base = min(n_rows, 32768)
+            if sample.dtype in (torch.float32, torch.bfloat16):
+                t[:base].copy_(torch.randn((base,) + shape[1:], generator=g))
+            elif sample.dtype == torch.uint8:
+                t[:base].copy_(torch.randint(0, 256, (base,) + shape[1:], generator=g, dtype=torch.uint8))
+            else:       # integer labels: same range as the sample rows
+                hi = int(sample.max().item()) + 1 if sample.numel() else 1
+                t[:base].copy_(torch.randint(0, max(hi, 2), (base,) + shape[1:], generator=g, dtype=sample.dtype))
+            for lo in range(base, n_rows, base):
+                t[lo:lo + base].copy_(t[:min(base, n_rows - lo)])
+            del t
+    dist.barrier()
+    cudart = torch.cuda.cudart()
+    for name, sample in sample_fields.items():
+        shape = (n_rows,) + tuple(sample.shape[1:])
+        t = torch.from_file(paths[name], shared=True, size=int(torch.tensor(shape).prod()),
+                            dtype=sample.dtype).view(shape)
+        rc = cudart.cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
+        assert int(rc) == 0, "cudaHostRegister failed: %s" % (rc,)
+        assert t.is_pinned()
+        out[name] = t
+    dist.barrier()
+    if rank == 0:
+        for path in paths.values():
+            os.unlink(path)                   # the mappings keep the memory alive
+    return out
+
+
+def nvls_parity_check(worker, step_fn, world, algo, precision):
+    """world > 1, after the timed region: ONE more step from the same weights, optimizer state and
+    batch, once through the fused NVLS kernel (K7: in-switch reduce + sharded update + multicast)
+    and once through ncclAllReduce + K2 (the un-fused path), eager launches both; reports the
+    difference of the resulting fp32 master weights and first optimizer-state vector and asserts
+    it is the reduction-order / bf16-rounding bound.  Driver-side evidence that the exchange every
+    multi-GPU number ran on computes what NCCL + the plain update computes."""
+    import torch
+    import torch.distributed as dist
+    pipe, opt, arena = worker.pipeline, worker.optimizer, worker.arena
+    nv = pipe.nvls
+    if nv is None:
+        return None
+    graphed, worker.graphed = worker.graphed, None
+    torch.cuda.synchronize()
+    pipe.sync_sharded_state()                      # master + state whole on every rank
+    names = list(opt._vec)
+    saved = {"master": arena.master.clone(), "lp": None if arena.lp is None else arena.lp.clone(),
+             "vec": {k: v.clone() for k, v in opt._vec.items()}, "steps": opt._steps}
+
+    def restore():
+        arena.master.copy_(saved["master"])
+        if arena.lp is not None:
+            arena.lp.copy_(saved["lp"])
+        for k, v in saved["vec"].items():
+            opt._vec[k].copy_(v)
+        opt._steps = saved["steps"]
+
+    def run():
+        step_fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        pipe.sync_sharded_state()
+        return arena.master.clone(), (opt._vec[names[0]].clone() if names else None)
+
+    try:
+        a_master, a_state = run()                  # K7
+        restore()
+        pipe.nvls = None
+        opt.nvls = None
+        b_master, b_state = run()                  # NCCL all-reduce in place + K2
+    finally:
+        pipe.nvls = nv
+        opt.nvls = nv
+        worker.graphed = graphed
+
+    def rel(a, b):
+        d = (a.double() - b.double())
+        return {"max_abs": float(d.abs().max()), "max_rel_to_peak": float(d.abs().max() / b.double().abs().max().clamp_min(1e-30)),
+                "rel_l2": float(d.norm() / b.double().norm().clamp_min(1e-30))}
+
+    res = {"what": "one step from identical state and batch: K7 (fused NVLS reduce+update+multicast) "
+                   "vs ncclAllReduce + K2, world %d, %s gradients" % (world, "bf16" if precision == "bf16" else "fp32"),
+           "master": rel(a_master, b_master)}
+    if a_state is not None:
+        res["state:" + names[0]] = rel(a_state, b_state)
+    # bounds: the update moves a weight by lr x (reduced gradient); the two reductions differ by
+    # summation order (fp32) or by where the bf16 rounding of the sum happens (bf16 gradients)
+    bound_master = 1e-4 if precision == "bf16" else 2e-6
+    bound_state = 2e-2 if precision == "bf16" else (1e-5 if algo == "sgd" else 1e-4)
+    res["bounds"] = {"master_max_rel_to_peak": bound_master, "state_rel_l2": bound_state}
+    ok = res["master"]["max_rel_to_peak"] <= bound_master
+    if a_state is not None:
+        ok = ok and res["state:" + names[0]]["rel_l2"] <= bound_state
+    res["ok"] = bool(ok)
+    flag = torch.tensor([0 if ok else 1], device=arena.device)
+    dist.all_reduce(flag)
+    assert int(flag.item()) == 0, "K7 vs NCCL+K2 parity check failed: %s" % json.dumps(res)
+    return res
 
 
 def main_b200(args, rank, local_rank, world):
@@ -223,7 +598,7 @@ def main_b200(args, rank, local_rank, world):
     torch.manual_seed(0)
     save_dir = "/tmp/frl_b200_bench_%d" % rank
     os.makedirs(save_dir, exist_ok=True)
-    problem = build_problem(ns, save_dir)
+    problem = build_problem(ns, save_dir, args)
     wargs = SolverWorkerArgs(run_opts=run_opts_for(ns, args.algo, B), problem=problem,
                              save_dir=save_dir, run_device=Device.GPU, node_idx=0, node_count=1,
                              rank=rank, local_rank=local_rank, world_size=world, group_name=None,
@@ -242,12 +617,7 @@ def main_b200(args, rank, local_rank, world):
     # ---- synthetic batches (generated on the device; seed 1234 + rank) ----
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     POOL = 4
-    pool = []
-    for _ in range(POOL):
-        x = torch.randn(B, WIDTH, device=dev, generator=gen)
-        y = torch.randint(0, N_CLASSES, (B,), device=dev, generator=gen)
-        r = torch.randn(B, REG_DIM, device=dev, generator=gen)
-        pool.append(([x], [(y,), (r,)]))
+    pool = [synthetic_batch(args, B, gen, dev) for _ in range(POOL)]
 
     def barrier():
         if world > 1:
@@ -393,33 +763,26 @@ def main_b200(args, rank, local_rank, world):
 
         from frl_b200.sampler import ScaffoldSampler
 
-        class LocalShardSampler(ScaffoldSampler):
-            """world > 1: every rank owns a node-local shard of the dataset and reshuffles it
-            per epoch (the ScaffoldSampler contract — set_epoch, permutation from a generator
-            seeded per epoch — on local indices; a global index space would need world x the
-            pinned memory per rank)."""
-
-            def __init__(self, n, seed):                    # no DistributedSampler bookkeeping
-                torch.utils.data.Sampler.__init__(self)
-                self.n, self.seed, self.epoch = n, seed, 0
-
-            def __len__(self):
-                return self.n
-
-            def rank_index_tensor(self):
-                g = torch.Generator().manual_seed(self.seed + self.epoch)
-                return torch.randperm(self.n, generator=g)
-
         L = K if K <= 128 else K // ((K + 127) // 128)        # steps per epoch
         n_epochs_timed = max(1, K // L)
-        n_host = L * B
-        host_problem = syn.make_mlp_problem(ns, save_dir, n_train=n_host, width=WIDTH,
-                                            n_classes=N_CLASSES, reg_dim=REG_DIM, depth=DEPTH,
-                                            pinned=True, fast_fields=True)
+        # the dataset: L x B samples per rank.  world > 1: ONE global dataset of L x B x world samples
+        # in shared host memory, page-locked by every rank, partitioned per epoch by the product's
+        # ScaffoldSampler (global randperm seeded by the epoch -> pad -> [rank::world], the
+        # reference's bit-exact partition) — every rank gathers ITS rows of the global array.
+        host_problem = build_problem(ns, save_dir, args, n_train=L * B if world == 1 else 8, pinned=True,
+                                     fast_fields=True, uint8=args.workload != "mlp")
         host_ds = host_problem.datasets[0]
         out_dtype = torch.bfloat16 if precision == Precision.BF16 else torch.float32
-        loader = DeviceBatchLoader(host_ds, batch_size=B, device=dev, out_dtype=out_dtype,
-                                   sampler=LocalShardSampler(n_host, 1000 * rank) if world > 1 else None)
+        if world > 1:
+            tolerant = getattr(host_ds.device_transform, "bf16_wire_fields", ()) if out_dtype == torch.bfloat16 else ()
+            host_ds.pinned_fields = shared_global_fields(host_ds.pinned_fields, L * B * world, rank, dev,
+                                                         bf16_fields=tuple(tolerant))
+            host_ds._n = L * B * world
+        sampler = None
+        if world > 1:
+            sampler = ScaffoldSampler(host_ds, shuffle_type=t.ShuffleType.RANDPERM, node_idx=0, node_count=1)
+        loader = DeviceBatchLoader(host_ds, batch_size=B, device=dev, out_dtype=out_dtype, sampler=sampler)
+        assert len(loader) == L, (len(loader), L)
         loaders = {t.Split.TRAIN: loader}
         h2d_bytes = loader.h2d_bytes_per_batch
         worker.cur_epoch = 1
@@ -455,23 +818,48 @@ def main_b200(args, rank, local_rank, world):
                "input_wire": {k: str(v).replace("torch.", "") for k, v in loader._wire_dtype.items()},
                "gpu_launches": e2e_launches,
                "epoch_losses": {k: float(v) for k, v in ep_losses.items()},
+               "sampler": ("ScaffoldSampler (global randperm seeded by the epoch, padded, [rank::world]) over "
+                           "one global dataset of %d samples in shared pinned host memory" % (L * B * world))
+                          if world > 1 else "RandomSampler (the reference's single-process loader)",
                "how": "SolverWorker._pass_one_epoch (the loop Solver.solve runs per epoch) over the "
-                      "Problem's dataset (fp32, %d batches) in pinned host memory: reference sampler "
+                      "Problem's dataset (%d batches per rank) in pinned host memory, model inputs stored in "
+                      "the wire dtype the dataset's transform declares (%s): sampler "
                       "indices -> DeviceBatchLoader moves the rows of the next batches to HBM while "
-                      "the current step runs (%s) -> transform + bf16 cast on device "
+                      "the current step runs (%s) -> transform + cast on device "
                       "(frl_preproc_affine) -> _pass_one_minibatch (CUDA-graph replay) -> loss row "
                       "written to pinned host memory by the criterion kernel, read 2 steps late; "
                       "includes the loop's retained-batch bookkeeping, the Problem's per-sample "
-                      "metric hook every 10 steps (D2H) and the epoch summary" % (
-                          L, "native host gather threads into pinned staging + one DMA per field"
+                      "metric hook every 10 steps and the epoch summary" % (
+                          L, ", ".join("%s %s" % (k, str(v).replace("torch.", "")) for k, v in loader._wire_dtype.items()),
+                          "native host gather threads into pinned staging + one DMA per field"
                           if loader.path == "host" else
                           "rows pulled over PCIe by frl_gather_rows%s on a copy stream" % (
                               "_tma" if loader.path == "tma" else ""))}
 
+    # ======================= K7 vs NCCL + K2 self-check (N > 1) =======================
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        worker.model.train()
+        worker.criterion.train()
+        parity = nvls_parity_check(worker, lambda: step_resident(W + K + 100), world, args.algo, args.precision)
+        barrier()
+
+    # ======================= stock PyTorch on the same GPU(s) =======================
+    torch_base = None
+    if not args.no_torch_baseline:
+        try:
+            torch_base = run_torch_gpu(args, rank, local_rank, world, steps=min(K, 20), warmup=5, with_e2e=False)
+            torch_base["speedup_of_value"] = value / torch_base["value"]
+        except Exception as e:                      # noqa: BLE001  (a comparison leg must not sink the line)
+            log("torch-gpu baseline failed:", repr(e))
+            torch_base = {"error": repr(e)[:200]}
+        barrier()
+
     # ======================= CPU baseline (rank 0, N=1) =======================
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        res = time_cpu_reference(args.algo, args.cpu_batch, args.cpu_steps, 1)
+        res = time_cpu_reference(args, args.cpu_batch or WORKLOADS[args.workload]["cpu_sample_batch"],
+                                 args.cpu_steps, 1)
         cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     nv = worker.pipeline.nvls
@@ -490,15 +878,17 @@ def main_b200(args, rank, local_rank, world):
                 "host_issue_ms_per_step": host_issue_ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if precision == Precision.BF16 else "f32", "data": "synthetic",
-                "config": {"workload": workload_name(B, args.algo), "global_batch": B * world,
+                "config": {"workload": workload_name(args), "global_batch": B * world,
                            "step_issue": "CUDA graph replay" if args.graph else "eager",
                            "parallelism": "dp%d" % world,
                            "precision": "bf16 forward/backward + bf16 grads, fp32 master weights and "
                                         "optimizer state" if precision == Precision.BF16 else "fp32",
-                           "l2": "no flush needed: each step streams the 54.7M-element arena "
-                                 "(>= 1.1 GB) and 4 rotating input batches, far larger than the 126 MB L2",
+                           "l2": "no flush needed: each step streams the %.1fM-element arena "
+                                 "(%.2f GB of update traffic) and 4 rotating input batches, larger than the "
+                                 "126 MB L2" % (arena.numel / 1e6, arena.numel * BYTES_PER_PARAM[(args.algo, args.precision)] / 1e9),
                            "grad_allreduce": grad_sync_desc},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+                "torch_gpu_baseline": torch_base, "parity_check": parity,
                 "clocks": clocks.summary(), "final_loss": float(losses[-1])}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -523,6 +913,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         main_reference(args, rank)
+        return
+    if args.impl == "torch-gpu":
+        main_torch_gpu(args, rank, local_rank, world)
         return
     if world != args.gpus:
         log("note: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world))

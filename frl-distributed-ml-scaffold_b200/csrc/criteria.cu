@@ -21,6 +21,8 @@ namespace frl {
 constexpr int kCThreads = 256;
 constexpr int kCWarps = kCThreads / 32;
 constexpr int kCMaxBlocksPerTask = 592;   // 148 SMs x 4
+constexpr int kCVecPerLane = 8;           // 4-element vectors a lane holds per row chunk
+constexpr int kCRowChunk = 32 * 4 * kCVecPerLane;   // 1024 columns: one register-resident chunk
 
 struct CritParams {
     frl_task_desc t[FRL_MAX_TASKS];
@@ -113,27 +115,61 @@ __device__ __forceinline__ void ce_partial(const frl_task_desc& t, int blk, int 
     for (int64_t row = static_cast<int64_t>(blk) * kCWarps + warp; row < t.rows;
          row += static_cast<int64_t>(nblk) * kCWarps) {
         const int64_t r0 = row * C;
-        // pass 1: row max
-        float m = -INFINITY;
-        if (vec) {
-            for (int64_t c = lane * 4; c < C; c += 128) {
-                const f32x4 v = ld4<OT>(t.out, r0 + c);
-                m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+        float m = -INFINITY, se = 0.f;
+        bool has_nan = false;
+        if (vec && C <= kCRowChunk) {
+            // the whole row in registers: every lane issues its (up to) 8 loads back to back, one
+            // trip to memory per row; max and sum(exp) are then formed exactly as in the two-pass
+            // form (max over the row first, then exp(x - max))
+            f32x4 v[kCVecPerLane];
+#pragma unroll
+            for (int j = 0; j < kCVecPerLane; ++j) {
+                const int64_t c = lane * 4 + j * 128;
+                v[j] = c < C ? ld4<OT>(t.out, r0 + c) : f32x4{-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             }
+#pragma unroll
+            for (int j = 0; j < kCVecPerLane; ++j)
+                m = fmaxf(fmaxf(m, fmaxf(v[j].x, v[j].y)), fmaxf(v[j].z, v[j].w));
+            m = warp_max(m);
+#pragma unroll
+            for (int j = 0; j < kCVecPerLane; ++j) {
+                if (lane * 4 + j * 128 < C) {
+                    has_nan |= (v[j].x != v[j].x) | (v[j].y != v[j].y) | (v[j].z != v[j].z) | (v[j].w != v[j].w);
+                    se += expf(v[j].x - m) + expf(v[j].y - m) + expf(v[j].z - m) + expf(v[j].w - m);
+                }
+            }
+        } else if (vec) {
+            // long rows: one pass, lane-local online softmax over chunks of kCRowChunk columns
+            // (running max / rescaled running sum per lane, combined across the warp at the end)
+            float mr = -INFINITY, sr = 0.f;
+            for (int64_t cb = 0; cb < C; cb += kCRowChunk) {
+                f32x4 v[kCVecPerLane];
+#pragma unroll
+                for (int j = 0; j < kCVecPerLane; ++j) {
+                    const int64_t c = cb + lane * 4 + j * 128;
+                    v[j] = c < C ? ld4<OT>(t.out, r0 + c) : f32x4{-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                }
+                float ml = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < kCVecPerLane; ++j)
+                    ml = fmaxf(fmaxf(ml, fmaxf(v[j].x, v[j].y)), fmaxf(v[j].z, v[j].w));
+                const float mn = fmaxf(mr, ml);
+                float add = 0.f;
+#pragma unroll
+                for (int j = 0; j < kCVecPerLane; ++j) {
+                    if (cb + lane * 4 + j * 128 < C) {
+                        has_nan |= (v[j].x != v[j].x) | (v[j].y != v[j].y) | (v[j].z != v[j].z) | (v[j].w != v[j].w);
+                        add += expf(v[j].x - mn) + expf(v[j].y - mn) + expf(v[j].z - mn) + expf(v[j].w - mn);
+                    }
+                }
+                sr = (mn == -INFINITY) ? 0.f : fmaf(sr, expf(mr - mn), add);
+                mr = mn;
+            }
+            m = warp_max(mr);
+            se = (mr == -INFINITY) ? 0.f : sr * expf(mr - m);
         } else {
             for (int64_t c = lane; c < C; c += 32) m = fmaxf(m, ldf<OT>(t.out, r0 + c));
-        }
-        m = warp_max(m);
-        // pass 2: sum exp(x - max)  (row is L1/L2 resident now)
-        float se = 0.f;
-        bool has_nan = false;
-        if (vec) {
-            for (int64_t c = lane * 4; c < C; c += 128) {
-                const f32x4 v = ld4<OT>(t.out, r0 + c);
-                has_nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
-                se += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
-            }
-        } else {
+            m = warp_max(m);
             for (int64_t c = lane; c < C; c += 32) {
                 const float x = ldf<OT>(t.out, r0 + c);
                 has_nan |= (x != x);
@@ -204,13 +240,13 @@ criteria_fwd_kernel(const __grid_constant__ CritParams P, float* __restrict__ lo
     if (!is_last) return;
     __threadfence();
 
-    // ---- final stage: one warp, fixed order ----
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
+    // ---- final stage: the whole CTA folds the per-CTA partials, fixed order, in double ----
+    __shared__ double dsm[kCWarps][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float total = 0.f;
     for (int i = 0; i < P.n_tasks; ++i) {
         double ds = 0.0, dsel = 0.0, dvalid = 0.0;
-        for (int b = lane; b < P.nblk[i]; b += 32) {
+        for (int b = threadIdx.x; b < P.nblk[i]; b += kCThreads) {
             ds += static_cast<double>(__ldcg(part_sum + P.part_off[i] + b));
             dsel += static_cast<double>(__ldcg(part_sel + P.part_off[i] + b));
             dvalid += static_cast<double>(__ldcg(part_valid + P.part_off[i] + b));
@@ -221,7 +257,13 @@ criteria_fwd_kernel(const __grid_constant__ CritParams P, float* __restrict__ lo
             dsel += __shfl_xor_sync(0xffffffffu, dsel, o);
             dvalid += __shfl_xor_sync(0xffffffffu, dvalid, o);
         }
-        if (lane == 0) {
+        __syncthreads();
+        if (lane == 0) { dsm[warp][0] = ds; dsm[warp][1] = dsel; dsm[warp][2] = dvalid; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ds = dsel = dvalid = 0.0;
+#pragma unroll
+            for (int w = 0; w < kCWarps; ++w) { ds += dsm[w][0]; dsel += dsm[w][1]; dvalid += dsm[w][2]; }
             const frl_task_desc& q = P.t[i];
             float Li;
             if (q.mask != nullptr && dsel == 0.0) {
@@ -237,7 +279,7 @@ criteria_fwd_kernel(const __grid_constant__ CritParams P, float* __restrict__ lo
             total += Li;
         }
     }
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         losses[0] = total;
         if (sink) sink[0] = total;
         if (nan_flag && (total != total)) *nan_flag = 1;
@@ -276,14 +318,25 @@ __device__ __forceinline__ void ce_bwd(const frl_task_desc& t, int blk, int nblk
         const float k = use ? coef : 0.f;
         const float l = lse[row];
         if (vec) {
-            for (int64_t c = lane * 4; c < C; c += 128) {
-                f32x4 v = ld4<OT>(t.out, r0 + c);
-                v.x = (expf(v.x - l) - (c + 0 == y ? 1.f : 0.f)) * k;
-                v.y = (expf(v.y - l) - (c + 1 == y ? 1.f : 0.f)) * k;
-                v.z = (expf(v.z - l) - (c + 2 == y ? 1.f : 0.f)) * k;
-                v.w = (expf(v.w - l) - (c + 3 == y ? 1.f : 0.f)) * k;
-                if (!use) v = f32x4{0.f, 0.f, 0.f, 0.f};     // 0 * NaN would leak NaNs
-                st4<OT>(t.dout, r0 + c, v);
+            for (int64_t cb = 0; cb < C; cb += kCRowChunk) {
+                f32x4 v[kCVecPerLane];
+#pragma unroll
+                for (int j = 0; j < kCVecPerLane; ++j) {        // all loads of the chunk first
+                    const int64_t c = cb + lane * 4 + j * 128;
+                    if (c < C) v[j] = ld4<OT>(t.out, r0 + c);
+                }
+#pragma unroll
+                for (int j = 0; j < kCVecPerLane; ++j) {
+                    const int64_t c = cb + lane * 4 + j * 128;
+                    if (c >= C) break;
+                    f32x4 q = v[j];
+                    q.x = (expf(q.x - l) - (c + 0 == y ? 1.f : 0.f)) * k;
+                    q.y = (expf(q.y - l) - (c + 1 == y ? 1.f : 0.f)) * k;
+                    q.z = (expf(q.z - l) - (c + 2 == y ? 1.f : 0.f)) * k;
+                    q.w = (expf(q.w - l) - (c + 3 == y ? 1.f : 0.f)) * k;
+                    if (!use) q = f32x4{0.f, 0.f, 0.f, 0.f};     // 0 * NaN would leak NaNs
+                    st4<OT>(t.dout, r0 + c, q);
+                }
             }
         } else {
             for (int64_t c = lane; c < C; c += 32) {

@@ -4,6 +4,8 @@
 // multitask_problem.py:56-71) and ships fp32 over a pageable copy.  Here the raw bytes are
 // shipped once (u8 / f32 / bf16) and one streaming pass normalises and converts the whole
 // batch: dst = src * scale[c] + bias[c], c = (i / inner) % channels.
+//
+// HBM-bound: read src once (1 / 2 / 4 B per element), write dst once (2 / 4 B).
 #include "frl_common.cuh"
 
 namespace frl {
@@ -19,45 +21,87 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-template <typename S, int N> struct alignas(sizeof(S) * N > 16 ? 16 : sizeof(S) * N) Pack { S v[N]; };
+// One ITEM = 16 bytes of source per thread: 4 fp32 / 8 bf16 / 16 u8 elements, converted and stored
+// as one 8-, 16- or 2x16-byte vector.  Every thread issues the loads of kPUnroll items before the
+// first use (64 B in flight per thread, ~128 KB per SM at full occupancy: what ~6.5 TB/s asks for).
+// The affine coefficients are resolved per ITEM, not per element: one channel covers the whole
+// item whenever `inner` is a multiple of the item width (images: H*W; flat fields: everything),
+// so the two integer divisions of the channel index are paid once per 16 source bytes and in
+// 32-bit arithmetic; ragged layouts take the per-element path.
+constexpr int kPUnroll = 4;
 
-// 8 elements per thread: u8 -> 8 B load, bf16 -> 16 B, f32 -> 2 x 16 B; stores 16 B / 2 x 16 B.
-template <typename S, typename D>
+template <typename S> struct Item { static constexpr int kElems = 16 / static_cast<int>(sizeof(S)); };
+
+template <typename S, int N> struct alignas(16) SrcVec { S v[N]; };
+template <typename D, int N> struct alignas(sizeof(D) * N >= 16 ? 16 : sizeof(D) * N) DstVec { D v[N]; };
+
+// MODE 0: x * uniform_scale; 1: one (scale, bias) pair for every element; 2: per channel, channel
+// constant within an item; 3: per channel, per element (ragged inner).
+template <typename S, typename D, int MODE>
 __global__ void __launch_bounds__(kPThreads)
-affine_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n, int64_t inner,
-              int64_t channels, const float* __restrict__ scale, const float* __restrict__ bias,
+affine_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n, uint32_t inner,
+              uint32_t channels, const float* __restrict__ scale, const float* __restrict__ bias,
               float uniform_scale) {
-    const int64_t n8 = n >> 3;
+    constexpr int E = Item<S>::kElems;
+    const int64_t n_items = n / E;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kPThreads;
-    const bool per_channel = (scale != nullptr) || (bias != nullptr);
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kPThreads + threadIdx.x; i < n8; i += stride) {
-        const Pack<S, 8> in = *reinterpret_cast<const Pack<S, 8>*>(src + (i << 3));
-        Pack<D, 8> out;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float x = to_f32<S>(in.v[k]);
-            if (per_channel) {
-                const int64_t c = (((i << 3) + k) / inner) % channels;
-                x = fmaf(x, scale ? __ldg(scale + c) : 1.f, bias ? __ldg(bias + c) : 0.f);
-            } else {
-                x *= uniform_scale;
-            }
-            out.v[k] = from_f32<D>(x);
-        }
-        *reinterpret_cast<Pack<D, 8>*>(dst + (i << 3)) = out;
+    float sc0 = uniform_scale, bi0 = 0.f;
+    if (MODE == 1) {
+        sc0 = scale ? __ldg(scale) : 1.f;
+        bi0 = bias ? __ldg(bias) : 0.f;
     }
-    // tail
-    if (blockIdx.x == 0) {
-        const int64_t e = (n8 << 3) + threadIdx.x;
-        if (threadIdx.x < 8 && e < n) {
-            float x = to_f32<S>(src[e]);
-            if (per_channel) {
-                const int64_t c = (e / inner) % channels;
-                x = fmaf(x, scale ? __ldg(scale + c) : 1.f, bias ? __ldg(bias + c) : 0.f);
-            } else {
-                x *= uniform_scale;
+    for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * kPThreads + threadIdx.x; i0 < n_items;
+         i0 += stride * kPUnroll) {
+        SrcVec<S, E> in[kPUnroll];
+#pragma unroll
+        for (int u = 0; u < kPUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n_items) in[u] = *reinterpret_cast<const SrcVec<S, E>*>(src + i * E);
+        }
+#pragma unroll
+        for (int u = 0; u < kPUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= n_items) break;
+            float sc = sc0, bi = bi0;
+            if (MODE == 2) {
+                const uint32_t c = (static_cast<uint32_t>(i * E) / inner) % channels;
+                sc = scale ? __ldg(scale + c) : 1.f;
+                bi = bias ? __ldg(bias + c) : 0.f;
             }
-            dst[e] = from_f32<D>(x);
+            DstVec<D, E> out;
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                float x = to_f32<S>(in[u].v[k]);
+                if (MODE == 3) {
+                    const int64_t c = ((i * E + k) / inner) % channels;
+                    sc = scale ? __ldg(scale + c) : 1.f;
+                    bi = bias ? __ldg(bias + c) : 0.f;
+                }
+                out.v[k] = from_f32<D>(MODE == 0 ? x * sc : fmaf(x, sc, bi));
+            }
+            if (sizeof(D) * E <= 16) {
+                *reinterpret_cast<DstVec<D, E>*>(dst + i * E) = out;
+            } else {          // 2 x 16 bytes (u8 -> bf16) or 4 x 16 (u8 -> f32)
+                constexpr int H = 16 / static_cast<int>(sizeof(D));
+#pragma unroll
+                for (int h = 0; h < E / H; ++h)
+                    *reinterpret_cast<DstVec<D, H>*>(dst + i * E + h * H) =
+                        *reinterpret_cast<const DstVec<D, H>*>(&out.v[h * H]);
+            }
+        }
+    }
+    // tail: n % E trailing elements
+    if (blockIdx.x == 0) {
+        const int64_t e = n_items * E + threadIdx.x;
+        if (threadIdx.x < E && e < n) {
+            float x = to_f32<S>(src[e]);
+            float sc = sc0, bi = bi0;
+            if (MODE >= 2) {
+                const int64_t c = (e / inner) % channels;
+                sc = scale ? __ldg(scale + c) : 1.f;
+                bi = bias ? __ldg(bias + c) : 0.f;
+            }
+            dst[e] = from_f32<D>(MODE == 0 ? x * sc : fmaf(x, sc, bi));
         }
     }
 }
@@ -66,12 +110,27 @@ template <typename S, typename D>
 static int launch_affine(const void* src, void* dst, int64_t n, int64_t inner, int64_t channels,
                          const float* scale, const float* bias, float uscale, cudaStream_t st,
                          const char* name) {
-    int64_t want = ((n >> 3) + kPThreads - 1) / kPThreads;
-    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+    constexpr int E = Item<S>::kElems;
+    int64_t want = (n / E + static_cast<int64_t>(kPThreads) * kPUnroll - 1) / (static_cast<int64_t>(kPThreads) * kPUnroll);
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;       // 8 x 256 threads per SM: one wave
     if (want > cap) want = cap;
     if (want < 1) want = 1;
-    affine_kernel<S, D><<<static_cast<int>(want), kPThreads, 0, st>>>(
-        static_cast<const S*>(src), static_cast<D*>(dst), n, inner, channels, scale, bias, uscale);
+    const bool per_channel = (scale != nullptr) || (bias != nullptr);
+    int mode = 0;
+    if (per_channel) {
+        if (channels == 1) mode = 1;
+        else if (inner % E == 0 && n < (1ll << 32) && inner < (1ll << 32) && channels < (1ll << 32)) mode = 2;
+        else mode = 3;
+    }
+#define FRL_AFF(M)                                                                                   \
+    affine_kernel<S, D, M><<<static_cast<int>(want), kPThreads, 0, st>>>(                            \
+        static_cast<const S*>(src), static_cast<D*>(dst), n, static_cast<uint32_t>(inner > 0xffffffffll ? 0xffffffffll : inner), \
+        static_cast<uint32_t>(channels), scale, bias, uscale)
+    if (mode == 0) FRL_AFF(0);
+    else if (mode == 1) FRL_AFF(1);
+    else if (mode == 2) FRL_AFF(2);
+    else FRL_AFF(3);
+#undef FRL_AFF
     return after_launch(name);
 }
 

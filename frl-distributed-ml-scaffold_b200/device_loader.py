@@ -141,15 +141,37 @@ class DeviceBatchLoader:
         if self.path not in ("host", "tma", "kernel"):
             raise ValueError(f"unknown input path {self.path!r}")
         self.blocks = int(os.environ.get("FRL_B200_INPUT_BLOCKS", "2" if self.path == "tma" else "16"))
-        # wire dtype per field: fp32 fields the transform declares bf16-tolerant travel as bf16 when
-        # the run computes in bf16 and FRL_B200_INPUT_WIRE=bf16 (host path: the gather threads convert)
-        self.wire = os.environ.get("FRL_B200_INPUT_WIRE", "native")
+        # wire dtype per field: fp32 fields the dataset's transform declares bf16-tolerant
+        # (``bf16_wire_fields``) travel over PCIe as bf16 when the run computes in bf16 — half the
+        # bytes of the step's dominant transfer.  FRL_B200_INPUT_WIRE: "auto" (default: do it),
+        # "native" (never), "bf16" (same as auto).  GPU-pulled paths read a bf16 copy of the field
+        # made ONCE here (the declared tolerance is the dataset author's statement that rounding
+        # the raw field is as good as rounding the transformed one); the host path converts while
+        # it gathers (the source may be a memory-mapped file that must stay as it is).
+        self.wire = os.environ.get("FRL_B200_INPUT_WIRE", "auto")
         tolerant = set(getattr(dataset.device_transform, "bf16_wire_fields", ()) or ())
         self._wire_dtype: Dict[str, torch.dtype] = {}
         for name, t in self._fields.items():
-            cvt = (self.wire == "bf16" and self.path == "host" and out_dtype == torch.bfloat16
+            cvt = (self.wire in ("auto", "bf16") and out_dtype == torch.bfloat16
                    and t.dtype == torch.float32 and name in tolerant)
             self._wire_dtype[name] = torch.bfloat16 if cvt else t.dtype
+        if self.path != "host":
+            converted = {}
+            cache = getattr(dataset, "_frl_wire_cache", None)
+            if cache is None:
+                cache = {}
+                try:
+                    dataset._frl_wire_cache = cache       # epochs / loaders of one run share it
+                except AttributeError:
+                    pass
+            for name, t in self._fields.items():
+                if self._wire_dtype[name] != t.dtype:
+                    key = (name, t.data_ptr(), self._wire_dtype[name])
+                    if key not in cache:
+                        cache[key] = t.to(self._wire_dtype[name]).pin_memory()
+                    converted[name] = cache[key]
+            if converted:
+                self._fields = {k: converted.get(k, v) for k, v in self._fields.items()}
         self._slots = []
         for _ in range(self.depth):
             slot = {name: torch.empty((batch_size,) + tuple(t.shape[1:]), dtype=self._wire_dtype[name],

@@ -90,6 +90,11 @@ class FusedArenaOptimizer(torch.optim.Optimizer):
     def begin_step(self) -> None:
         """Open step ``_steps + 1``; per-bucket ``apply_range`` calls share its number."""
         self._in_step = True
+        # an EAGER step after a graph was captured (ragged last batch, a second batch signature):
+        # the kernels still read the device-resident scalars, so they must be this step's.  Never
+        # inside a capture: the copy would be frozen into the graph and undo the per-replay upload.
+        if self._dyn is not None and not (self._dyn.is_cuda and torch.cuda.is_current_stream_capturing()):
+            self.refresh_dynamic_scalars()
 
     def end_step(self) -> None:
         self._steps += 1

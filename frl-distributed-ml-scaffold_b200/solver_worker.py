@@ -442,7 +442,14 @@ class SolverWorker:
         log_freq = self.run_opts.lossLoggingFreq
         dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
 
+        trace = [] if os.environ.get("FRL_B200_EPOCH_TRACE") else None
+
+        def mark(what: str) -> None:
+            if trace is not None:
+                trace.append((what, time.perf_counter()))
+
         for data_type, loader in loaders.items():
+            mark("split start")
             if dist_on:
                 loader.sampler.set_epoch(self.cur_epoch)
             # the planned order goes to the (null) cache accessor; drawing it also keeps the
@@ -465,10 +472,13 @@ class SolverWorker:
             log = LossLog(n_tasks, n_batches, self.device)
             checked = 0
             batch_start = time.time()
+            mark("setup done")
 
             with StepWatchdog(self.run_opts.minibatchTimeoutMs) as dog, sampler_state:
                 for minibatch_idx, (data, target, raw_meta) in enumerate(loader):
                     dog.kick()
+                    if minibatch_idx < 3:
+                        mark("batch %d served" % minibatch_idx)
                     data = [t if t.is_cuda else t.to(self.device, non_blocking=True) for t in data]
                     target = [tuple(t if t.is_cuda else t.to(self.device, non_blocking=True)
                                     for t in head) for head in target]
@@ -510,8 +520,10 @@ class SolverWorker:
                     timer.batch.update(time.time() - batch_start)
                     batch_start = time.time()
 
+                mark("last step issued")
                 if self.device.type == "cuda":
                     torch.cuda.current_stream().synchronize()
+                mark("stream drained")
                 while checked < n_batches:
                     self._raise_if_nan(log, checked, data_type)
                     checked += 1
@@ -524,8 +536,15 @@ class SolverWorker:
                           for i, name in enumerate(names)}
             # per-step [total, sub-losses...] of every split, in the order they were run
             self.loss_history.append((self.cur_epoch, data_type, per_step.copy()))
+            mark("metrics joined")
             epoch_stats[data_type] = self._epoch_summary(
                 problem, sampler_state, dataset, split_loss, timer, mode)
+            mark("summary done")
+            if trace:
+                t0 = trace[0][1]
+                logger.info("epoch trace (ms since split start): " + ", ".join(
+                    "%s %.2f" % (w, 1e3 * (ts - t0)) for w, ts in trace))
+                trace.clear()
 
         if self.run_opts.debugGrad:
             logger.info("Task grad contributions: " + ", ".join(

@@ -1,8 +1,10 @@
-"""Import the UNMODIFIED reference (``/root/reference``) as the package ``frldistml.scaffold``.
+"""Import the UNMODIFIED reference as the package ``frldistml.scaffold``.
 
-TEST INFRASTRUCTURE.  Works only where ``/root/reference`` exists (the build container, not
-the GPU box); used by ``oracle/make_golden.py`` to generate the committed fixtures and by the
-``-m "not gpu"`` tests that pin ``oracle/ref_loop.py`` against the live reference.
+TEST INFRASTRUCTURE.  Source: ``/root/reference`` where it exists (the build container), else the
+archive ``oracle/build_ref.py`` packed into the git-ignored ``oracle/_ref/reference.zip`` (which
+travels to the GPU box); used by ``oracle/make_golden.py`` to generate the committed fixtures, by
+the ``-m reference`` tests that pin ``oracle/ref_loop.py`` against the live reference and by the
+CPU arm of ``bench.py``.
 
 What the shim does, without touching the reference tree:
   * a temp dir with ``frldistml/__init__.py`` and a symlink ``frldistml/scaffold -> /root/reference``
@@ -17,11 +19,16 @@ import tempfile
 import types
 
 REFERENCE_DIR = "/root/reference"
+REFERENCE_ZIP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference.zip")
 _state = {}
 
 
-def reference_available() -> bool:
+def _tree_available() -> bool:
     return os.path.isdir(REFERENCE_DIR) and os.path.exists(os.path.join(REFERENCE_DIR, "solver.py"))
+
+
+def reference_available() -> bool:
+    return _tree_available() or os.path.exists(REFERENCE_ZIP)
 
 
 def _stub_module(name: str, **attrs) -> types.ModuleType:
@@ -37,7 +44,7 @@ def import_reference():
     if "pkg" in _state:
         return _state["pkg"]
     if not reference_available():
-        raise RuntimeError("/root/reference is not present on this machine")
+        raise RuntimeError("the reference is neither at /root/reference nor installed in oracle/_ref")
     os.environ["TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD"] = "1"
 
     if "plotly" not in sys.modules:
@@ -59,12 +66,15 @@ def import_reference():
     # real reference
     for k in [k for k in sys.modules if k == "frldistml" or k.startswith("frldistml.")]:
         del sys.modules[k]
-    root = tempfile.mkdtemp(prefix="frl_ref_shim_")
-    os.makedirs(os.path.join(root, "frldistml"))
-    open(os.path.join(root, "frldistml", "__init__.py"), "w").close()
-    os.symlink(REFERENCE_DIR, os.path.join(root, "frldistml", "scaffold"))
-    sys.path.insert(0, root)
-    sys.dont_write_bytecode = True         # /root/reference is read-only
+    if _tree_available():
+        root = tempfile.mkdtemp(prefix="frl_ref_shim_")
+        os.makedirs(os.path.join(root, "frldistml"))
+        open(os.path.join(root, "frldistml", "__init__.py"), "w").close()
+        os.symlink(REFERENCE_DIR, os.path.join(root, "frldistml", "scaffold"))
+        sys.path.insert(0, root)
+        sys.dont_write_bytecode = True         # /root/reference is read-only
+    else:
+        sys.path.insert(0, REFERENCE_ZIP)      # zipimport: frldistml/scaffold/*.py inside
     import importlib
     pkg = importlib.import_module("frldistml.scaffold")
     for name in ("types", "criteria", "model", "lr_scheduler", "sampler", "transform", "task",
