@@ -37,6 +37,12 @@ class TaskDesc(C.Structure):
     ]
 
 
+class GradSeg(C.Structure):
+    """Mirror of ``frl_grad_seg``."""
+    _fields_ = [("g", C.c_void_p), ("arena_off", C.c_int64), ("numel", C.c_int64),
+                ("g_dtype", C.c_int32), ("_pad", C.c_int32)]
+
+
 # name -> (restype, argtypes); every name here must be declared in include/frl_b200.h
 _vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 SIGNATURES = {
@@ -49,6 +55,11 @@ SIGNATURES = {
     "frl_sgd_momentum": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _vp, _vp, _i, _i, _vp]),
     "frl_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i64, _d, _vp, _vp, _i, _vp]),
     "frl_rmsprop": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _d, _vp, _vp, _i, _vp]),
+    "frl_mt_tile_elems": (_i64, []),
+    "frl_flatten_grads": (_i, [_vp, _vp, _i, _i64, _vp, _i, _d, _vp]),
+    "frl_sgd_momentum_mt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _d, _d, _d, _d, _d, _vp, _vp, _i, _vp]),
+    "frl_adam_mt": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _d, _d, _d, _d, _d, _i64, _d, _vp, _vp, _vp]),
+    "frl_rmsprop_mt": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _d, _d, _d, _d, _d, _d, _vp, _vp, _vp]),
     "frl_reduce_scratch_bytes": (_i64, []),
     "frl_grad_sumsq_clip": (_i, [_vp, _i64, _i, _f, _f, _vp, _vp, _vp]),
     "frl_criteria_scratch_bytes": (_i64, [_i]),
@@ -163,6 +174,42 @@ def rmsprop(p, g, sq, buf, p_lp, n, *, lr, alpha, eps, wd, mu, grad_scale=1.0,
     _check(lib().frl_rmsprop(_ptr(p), _ptr(g), _ptr(sq), _ptr(buf), _ptr(p_lp), n, lr, alpha,
                              eps, wd, mu, grad_scale, _ptr(grad_scale_dev), _ptr(dyn),
                              dtype_code(g.dtype), _stream()), "frl_rmsprop")
+
+
+# ---- K2-mt / K1: multi-tensor forms (gradients read where autograd left them) ---------------------
+
+def mt_tile_elems() -> int:
+    return int(lib().frl_mt_tile_elems())
+
+
+def flatten_grads(table, arena_grad, *, scale: float = 1.0) -> None:
+    """arena_grad[seg.arena_off + i] = cast(seg.g[i] * scale) for every segment of ``table``
+    (a ``multi_tensor.GradSegTable`` whose device copy is current): one launch."""
+    _check(lib().frl_flatten_grads(table.segs_dev_ptr, table.prefix_dev_ptr, table.n_segs, table.n_tiles,
+                                   _ptr(arena_grad), dtype_code(arena_grad.dtype), scale, _stream()),
+           "frl_flatten_grads")
+
+
+def sgd_momentum_mt(p, buf, p_lp, table, *, lr, mu, dampening, wd, grad_scale=1.0, grad_scale_dev=None,
+                    first_step=False, dyn=None) -> None:
+    _check(lib().frl_sgd_momentum_mt(_ptr(p), _ptr(buf), _ptr(p_lp), table.segs_dev_ptr, table.prefix_dev_ptr,
+                                     table.n_segs, table.n_tiles, lr, mu, dampening, wd, grad_scale,
+                                     _ptr(grad_scale_dev), _ptr(dyn), int(first_step), _stream()),
+           "frl_sgd_momentum_mt")
+
+
+def adam_mt(p, m, v, vmax, p_lp, table, *, lr, beta1, beta2, eps, wd, step, grad_scale=1.0,
+            grad_scale_dev=None, dyn=None) -> None:
+    _check(lib().frl_adam_mt(_ptr(p), _ptr(m), _ptr(v), _ptr(vmax), _ptr(p_lp), table.segs_dev_ptr,
+                             table.prefix_dev_ptr, table.n_segs, table.n_tiles, lr, beta1, beta2, eps, wd,
+                             step, grad_scale, _ptr(grad_scale_dev), _ptr(dyn), _stream()), "frl_adam_mt")
+
+
+def rmsprop_mt(p, sq, buf, p_lp, table, *, lr, alpha, eps, wd, mu, grad_scale=1.0, grad_scale_dev=None,
+               dyn=None) -> None:
+    _check(lib().frl_rmsprop_mt(_ptr(p), _ptr(sq), _ptr(buf), _ptr(p_lp), table.segs_dev_ptr,
+                                table.prefix_dev_ptr, table.n_segs, table.n_tiles, lr, alpha, eps, wd, mu,
+                                grad_scale, _ptr(grad_scale_dev), _ptr(dyn), _stream()), "frl_rmsprop_mt")
 
 
 # ---- K3 -------------------------------------------------------------------------------------

@@ -155,6 +155,180 @@ static int launch_update(const Rule& rule, float* p, const void* g, float* s0, f
     return after_launch(name);
 }
 
+
+// =============================================================================================
+// K2-mt / K1 — multi-tensor forms: gradients read in place from wherever autograd produced them
+// =============================================================================================
+// Convolution and normalisation layers hand their parameter gradients to autograd as freshly
+// allocated tensors (cuDNN writes them; there is no `out=`).  The stock pipeline then copies every
+// one of them into a DDP bucket and back (reference solver.py:287-289 -> torch Reducer: +16 B per
+// parameter and a copy launch per tensor).  Here a SEGMENT TABLE in device memory
+// (frl_grad_seg: gradient pointer + dtype + arena offset + length per parameter tensor) lets
+//   * frl_*_mt        : the fused update read each gradient where it lies (1 GPU: the flatten
+//                       pass does not exist at all, the arena's `grad` vector is not touched);
+//   * frl_flatten_grads: ONE launch per bucket gather the bucket's gradients into the arena slice
+//                       NCCL / the NVLS kernel reduce (world > 1: copy-in only, cast and pre-scale
+//                       folded in, no copy-out, no per-tensor launches).
+// Work is cut into tiles of kTileElems arena elements that never straddle a segment;
+// tile_prefix[s] = first tile of segment s (n_segs + 1 entries).  A CTA finds its segment by
+// binary search in that (L1-resident, <= 2 KB) array: ~8 probes per 16 KB+ of streamed data.
+constexpr int kTileElems = kTileVec * 4;
+
+struct SegView {
+    const void* g;
+    int64_t arena_off, numel;
+    int g_dtype;
+    int64_t t_in;      // tile index inside the segment
+};
+
+__device__ __forceinline__ SegView find_segment(const frl_grad_seg* __restrict__ segs,
+                                                const int64_t* __restrict__ tile_prefix, int n_segs,
+                                                int64_t tile) {
+    int lo = 0, hi = n_segs;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(tile_prefix + mid) <= tile) lo = mid; else hi = mid;
+    }
+    SegView v;
+    v.g = segs[lo].g;
+    v.arena_off = segs[lo].arena_off;
+    v.numel = segs[lo].numel;
+    v.g_dtype = segs[lo].g_dtype;
+    v.t_in = tile - __ldg(tile_prefix + lo);
+    return v;
+}
+
+// 4 consecutive gradient elements starting at element e of a segment, zero-filled past its end
+__device__ __forceinline__ f32x4 seg_load4(const SegView& sv, int64_t e) {
+    if (e + 4 <= sv.numel) {
+        if (sv.g_dtype == FRL_F32) return ld_stream_ro(reinterpret_cast<const f32x4*>(static_cast<const float*>(sv.g) + e));
+        const bf16x4 r = ld_stream_ro(reinterpret_cast<const bf16x4*>(static_cast<const __nv_bfloat16*>(sv.g) + e));
+        return f32x4{bf16lo(r.a), bf16hi(r.a), bf16lo(r.b), bf16hi(r.b)};
+    }
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (e + k < sv.numel)
+            t[k] = sv.g_dtype == FRL_F32 ? static_cast<const float*>(sv.g)[e + k]
+                                         : __bfloat162float(static_cast<const __nv_bfloat16*>(sv.g)[e + k]);
+    return f32x4{t[0], t[1], t[2], t[3]};
+}
+
+template <typename Rule, int NS, bool HAS_LP>
+__global__ void __launch_bounds__(kThreads)
+update_mt_kernel(float* __restrict__ p_, float* __restrict__ s0_, float* __restrict__ s1_,
+                 float* __restrict__ s2_, bf16x4* __restrict__ lp,
+                 const frl_grad_seg* __restrict__ segs, const int64_t* __restrict__ tile_prefix,
+                 int n_segs, int64_t n_tiles, Rule rule, float gscale,
+                 const float* __restrict__ gscale_dev, const float* __restrict__ dyn) {
+    if (dyn) rule.patch(dyn);
+    f32x4* p = reinterpret_cast<f32x4*>(p_);
+    f32x4* s0 = reinterpret_cast<f32x4*>(s0_);
+    f32x4* s1 = reinterpret_cast<f32x4*>(s1_);
+    f32x4* s2 = reinterpret_cast<f32x4*>(s2_);
+    const float gs = gscale_dev ? gscale * __ldg(gscale_dev) : gscale;
+    const f32x4 zero{0.f, 0.f, 0.f, 0.f};
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const SegView sv = find_segment(segs, tile_prefix, n_segs, tile);
+        const int64_t seg_vec = (sv.numel + 3) >> 2;              // arena slices are padded to 8
+        const int64_t v0 = sv.t_in * kTileVec + threadIdx.x;      // vec4 index inside the segment
+        const int64_t a0 = sv.arena_off >> 2;                     // vec4 index of the segment in the arena
+        f32x4 vp[kUnroll], vg[kUnroll], a_0[kUnroll], a_1[kUnroll], a_2[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const int64_t v = v0 + j * kThreads;
+            if (v < seg_vec) {
+                const int64_t i = a0 + v;
+                vg[j] = seg_load4(sv, v << 2);
+                vp[j] = ld_stream(p + i);
+                a_0[j] = NS > 0 ? ld_stream(s0 + i) : zero;
+                a_1[j] = NS > 1 ? ld_stream(s1 + i) : zero;
+                a_2[j] = NS > 2 ? ld_stream(s2 + i) : zero;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const int64_t v = v0 + j * kThreads;
+            if (v >= seg_vec) break;
+            const int64_t i = a0 + v;
+            apply4(rule, vp[j], vg[j], gs, a_0[j], a_1[j], a_2[j]);
+            st_stream(p + i, vp[j]);
+            if (NS > 0) st_stream(s0 + i, a_0[j]);
+            if (NS > 1) st_stream(s1 + i, a_1[j]);
+            if (NS > 2) st_stream(s2 + i, a_2[j]);
+            if (HAS_LP) st_stream(lp + i, bf16x4{pack_bf16(vp[j].x, vp[j].y), pack_bf16(vp[j].z, vp[j].w)});
+        }
+    }
+}
+
+template <typename DVec>
+__device__ __forceinline__ void store_flat4(DVec* dst, int64_t i, const f32x4& v);
+template <> __device__ __forceinline__ void store_flat4<f32x4>(f32x4* dst, int64_t i, const f32x4& v) {
+    st_stream(dst + i, v);
+}
+template <> __device__ __forceinline__ void store_flat4<bf16x4>(bf16x4* dst, int64_t i, const f32x4& v) {
+    st_stream(dst + i, bf16x4{pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)});
+}
+
+template <typename DVec>
+__global__ void __launch_bounds__(kThreads)
+flatten_kernel(DVec* __restrict__ dst, const frl_grad_seg* __restrict__ segs,
+               const int64_t* __restrict__ tile_prefix, int n_segs, int64_t n_tiles, float scale) {
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const SegView sv = find_segment(segs, tile_prefix, n_segs, tile);
+        const int64_t seg_vec = (sv.numel + 3) >> 2;
+        const int64_t v0 = sv.t_in * kTileVec + threadIdx.x;
+        const int64_t a0 = sv.arena_off >> 2;
+        f32x4 vg[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const int64_t v = v0 + j * kThreads;
+            if (v < seg_vec) vg[j] = seg_load4(sv, v << 2);
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const int64_t v = v0 + j * kThreads;
+            if (v >= seg_vec) break;
+            f32x4 q = vg[j];
+            if (scale != 1.f) { q.x *= scale; q.y *= scale; q.z *= scale; q.w *= scale; }
+            store_flat4<DVec>(dst, a0 + v, q);
+        }
+    }
+}
+
+template <typename K>
+static int grid_for_tiles(K kernel, int64_t n_tiles) {
+    static int occ = 0;
+    if (occ == 0) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, kThreads, 0) != cudaSuccess || o < 1) o = 2;
+        occ = o;
+    }
+    const int64_t cap = static_cast<int64_t>(sm_count()) * occ;
+    const int64_t g = n_tiles < cap ? n_tiles : cap;
+    return g < 1 ? 1 : static_cast<int>(g);
+}
+
+template <typename Rule, int NS>
+static int launch_update_mt(const Rule& rule, float* p, float* s0, float* s1, float* s2, void* p_lp,
+                            const frl_grad_seg* segs, const int64_t* tile_prefix, int n_segs,
+                            int64_t n_tiles, float gscale, const float* gscale_dev, const float* dyn,
+                            cudaStream_t st, const char* name) {
+    FRL_REQUIRE(n_segs >= 0 && n_tiles >= 0, FRL_E_ARG, "%s: negative counts", name);
+    if (n_segs == 0 || n_tiles == 0) return 0;
+    FRL_REQUIRE(p && segs && tile_prefix, FRL_E_ARG, "%s: null p/segs/tile_prefix", name);
+    FRL_REQUIRE(aligned16(p) && aligned16(s0) && aligned16(s1) && aligned16(s2) && aligned16(p_lp),
+                FRL_E_ALIGN, "%s: arrays must be 16-byte aligned", name);
+    bf16x4* lp = static_cast<bf16x4*>(p_lp);
+    if (lp)
+        update_mt_kernel<Rule, NS, true><<<grid_for_tiles(update_mt_kernel<Rule, NS, true>, n_tiles), kThreads, 0, st>>>(
+            p, s0, s1, s2, lp, segs, tile_prefix, n_segs, n_tiles, rule, gscale, gscale_dev, dyn);
+    else
+        update_mt_kernel<Rule, NS, false><<<grid_for_tiles(update_mt_kernel<Rule, NS, false>, n_tiles), kThreads, 0, st>>>(
+            p, s0, s1, s2, lp, segs, tile_prefix, n_segs, n_tiles, rule, gscale, gscale_dev, dyn);
+    return after_launch(name);
+}
+
 }  // namespace frl
 
 using namespace frl;
@@ -220,4 +394,75 @@ extern "C" int frl_rmsprop(float* p, const void* g, float* sq, float* buf, void*
     RmspropRule<false> r{af, oma, epsf, wdf, muf, nlr};
     return launch_update<RmspropRule<false>, 1>(r, p, g, sq, nullptr, nullptr, p_lp, n, gs,
                                                 grad_scale_dev, dyn, g_dtype, st, "frl_rmsprop");
+}
+
+// ---- multi-tensor entry points -------------------------------------------------------------------
+
+extern "C" int64_t frl_mt_tile_elems(void) { return kTileElems; }
+
+extern "C" int frl_flatten_grads(const frl_grad_seg* segs_dev, const int64_t* tile_prefix_dev, int n_segs,
+                                 int64_t n_tiles, void* arena_grad, int dst_dtype, double scale, void* stream) {
+    FRL_REQUIRE(n_segs >= 0 && n_tiles >= 0, FRL_E_ARG, "frl_flatten_grads: negative counts");
+    if (n_segs == 0 || n_tiles == 0) return 0;
+    FRL_REQUIRE(segs_dev && tile_prefix_dev && arena_grad, FRL_E_ARG, "frl_flatten_grads: null pointer");
+    FRL_REQUIRE(dst_dtype == FRL_F32 || dst_dtype == FRL_BF16, FRL_E_DTYPE, "frl_flatten_grads: dst dtype %d", dst_dtype);
+    FRL_REQUIRE(aligned16(arena_grad), FRL_E_ALIGN, "frl_flatten_grads: arena must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float sc = static_cast<float>(scale);
+    if (dst_dtype == FRL_F32)
+        flatten_kernel<f32x4><<<grid_for_tiles(flatten_kernel<f32x4>, n_tiles), kThreads, 0, st>>>(
+            static_cast<f32x4*>(arena_grad), segs_dev, tile_prefix_dev, n_segs, n_tiles, sc);
+    else
+        flatten_kernel<bf16x4><<<grid_for_tiles(flatten_kernel<bf16x4>, n_tiles), kThreads, 0, st>>>(
+            static_cast<bf16x4*>(arena_grad), segs_dev, tile_prefix_dev, n_segs, n_tiles, sc);
+    return after_launch("frl_flatten_grads");
+}
+
+extern "C" int frl_sgd_momentum_mt(float* p, float* buf, void* p_lp, const frl_grad_seg* segs_dev,
+                                   const int64_t* tile_prefix_dev, int n_segs, int64_t n_tiles,
+                                   double lr, double mu, double dampening, double wd, double grad_scale,
+                                   const float* grad_scale_dev, const float* dyn, int first_step, void* stream) {
+    FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_sgd_momentum_mt: momentum needs buf");
+    const SgdRule r = make_sgd_rule(lr, mu, dampening, wd, first_step);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float gs = static_cast<float>(grad_scale);
+    if (mu != 0.0)
+        return launch_update_mt<SgdRule, 1>(r, p, buf, nullptr, nullptr, p_lp, segs_dev, tile_prefix_dev, n_segs,
+                                            n_tiles, gs, grad_scale_dev, dyn, st, "frl_sgd_momentum_mt");
+    return launch_update_mt<SgdRule, 0>(r, p, nullptr, nullptr, nullptr, p_lp, segs_dev, tile_prefix_dev, n_segs,
+                                        n_tiles, gs, grad_scale_dev, dyn, st, "frl_sgd_momentum_mt");
+}
+
+extern "C" int frl_adam_mt(float* p, float* m, float* v, float* vmax, void* p_lp, const frl_grad_seg* segs_dev,
+                           const int64_t* tile_prefix_dev, int n_segs, int64_t n_tiles, double lr, double beta1,
+                           double beta2, double eps, double wd, int64_t step, double grad_scale,
+                           const float* grad_scale_dev, const float* dyn, void* stream) {
+    FRL_REQUIRE(m && v, FRL_E_ARG, "frl_adam_mt: null state");
+    FRL_REQUIRE(step >= 1, FRL_E_ARG, "frl_adam_mt: step must be >= 1");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float gs = static_cast<float>(grad_scale);
+    if (vmax)
+        return launch_update_mt<AdamRule<true>, 3>(make_adam_rule<true>(lr, beta1, beta2, eps, wd, step), p, m, v, vmax,
+                                                   p_lp, segs_dev, tile_prefix_dev, n_segs, n_tiles, gs,
+                                                   grad_scale_dev, dyn, st, "frl_adam_mt");
+    return launch_update_mt<AdamRule<false>, 2>(make_adam_rule<false>(lr, beta1, beta2, eps, wd, step), p, m, v, nullptr,
+                                                p_lp, segs_dev, tile_prefix_dev, n_segs, n_tiles, gs,
+                                                grad_scale_dev, dyn, st, "frl_adam_mt");
+}
+
+extern "C" int frl_rmsprop_mt(float* p, float* sq, float* buf, void* p_lp, const frl_grad_seg* segs_dev,
+                              const int64_t* tile_prefix_dev, int n_segs, int64_t n_tiles, double lr, double alpha,
+                              double eps, double wd, double mu, double grad_scale, const float* grad_scale_dev,
+                              const float* dyn, void* stream) {
+    FRL_REQUIRE(sq, FRL_E_ARG, "frl_rmsprop_mt: null sq");
+    FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_rmsprop_mt: momentum needs buf");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float gs = static_cast<float>(grad_scale);
+    if (mu != 0.0)
+        return launch_update_mt<RmspropRule<true>, 2>(make_rmsprop_rule<true>(lr, alpha, eps, wd, mu), p, sq, buf, nullptr,
+                                                      p_lp, segs_dev, tile_prefix_dev, n_segs, n_tiles, gs,
+                                                      grad_scale_dev, dyn, st, "frl_rmsprop_mt");
+    return launch_update_mt<RmspropRule<false>, 1>(make_rmsprop_rule<false>(lr, alpha, eps, wd, mu), p, sq, nullptr, nullptr,
+                                                   p_lp, segs_dev, tile_prefix_dev, n_segs, n_tiles, gs,
+                                                   grad_scale_dev, dyn, st, "frl_rmsprop_mt");
 }

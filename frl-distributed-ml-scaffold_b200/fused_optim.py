@@ -118,6 +118,15 @@ class FusedArenaOptimizer(torch.optim.Optimizer):
     def _launch(self, lo: int, hi: int, grad_scale: float, coef) -> None:
         raise NotImplementedError
 
+    def apply_table(self, table, *, grad_scale: float = 1.0) -> None:
+        """Update every arena slot listed in ``table`` (a ``multi_tensor.GradSegTable`` whose device
+        copy is current), reading each gradient where the table says it lies (K2-mt)."""
+        if table.n_segs:
+            self._launch_mt(table, grad_scale)
+
+    def _launch_mt(self, table, grad_scale: float) -> None:
+        raise NotImplementedError
+
     # -- fused all-reduce + update + broadcast (K7) ------------------------------------------------
     def apply_range_nvls(self, lo: int, hi: int, *, grad_scale: float) -> None:
         if hi > lo:
@@ -229,6 +238,14 @@ class FusedSGD(FusedArenaOptimizer):
                              grad_scale=grad_scale, grad_scale_dev=coef,
                              first_step=(self._steps == 0), dyn=self._dyn)
 
+    def _launch_mt(self, table, grad_scale):
+        h = self.hyper
+        mu = float(h["momentum"])
+        KERNELS.sgd_momentum_mt(self.arena.master, self._state("momentum_buffer") if mu != 0.0 else None,
+                                self.arena.lp, table, lr=float(h["lr"]), mu=mu,
+                                dampening=float(h["dampening"]), wd=float(h["weight_decay"]),
+                                grad_scale=grad_scale, first_step=(self._steps == 0), dyn=self._dyn)
+
     def _launch_nvls(self, lo, hi, grad_scale):
         h = self.hyper
         mu = float(h["momentum"])
@@ -271,6 +288,14 @@ class FusedAdam(FusedArenaOptimizer):
                      wd=float(h["weight_decay"]), step=self._steps + 1,
                      grad_scale=grad_scale, grad_scale_dev=coef, dyn=self._dyn)
 
+    def _launch_mt(self, table, grad_scale):
+        h = self.hyper
+        KERNELS.adam_mt(self.arena.master, self._state("exp_avg"), self._state("exp_avg_sq"),
+                        self._state("max_exp_avg_sq") if h["amsgrad"] else None, self.arena.lp, table,
+                        lr=float(h["lr"]), beta1=float(h["betas"][0]), beta2=float(h["betas"][1]),
+                        eps=float(h["eps"]), wd=float(h["weight_decay"]), step=self._steps + 1,
+                        grad_scale=grad_scale, dyn=self._dyn)
+
     def _launch_nvls(self, lo, hi, grad_scale):
         h = self.hyper
         mc_g, mc_out = self._nvls_ptrs(lo)
@@ -303,6 +328,14 @@ class FusedRMSprop(FusedArenaOptimizer):
                         lr=float(h["lr"]), alpha=float(h["alpha"]), eps=float(h["eps"]),
                         wd=float(h["weight_decay"]), mu=mu, grad_scale=grad_scale,
                         grad_scale_dev=coef, dyn=self._dyn)
+
+    def _launch_mt(self, table, grad_scale):
+        h = self.hyper
+        mu = float(h["momentum"])
+        KERNELS.rmsprop_mt(self.arena.master, self._state("square_avg"),
+                           self._state("momentum_buffer") if mu != 0.0 else None, self.arena.lp, table,
+                           lr=float(h["lr"]), alpha=float(h["alpha"]), eps=float(h["eps"]),
+                           wd=float(h["weight_decay"]), mu=mu, grad_scale=grad_scale, dyn=self._dyn)
 
     def _launch_nvls(self, lo, hi, grad_scale):
         h = self.hyper

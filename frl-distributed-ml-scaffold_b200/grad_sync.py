@@ -4,17 +4,21 @@ Stands where the reference wraps the model in ``DistributedDataParallel`` (refer
 solver.py:265-294) and later calls ``clip_grad_norm_`` / ``optimizer.step()`` (reference
 solver_worker.py:585-592).  Differences that matter on B200:
 
-* gradients land in the flat ``grad`` arena as soon as autograd produces them (a
-  post-accumulate hook per parameter; ``nn.Linear`` weight gradients are written there directly
-  by ``arena_linear``), so a bucket is a contiguous slice NCCL reduces **in place** — no bucket
-  copy-in, no copy-out;
+* ``nn.Linear`` gradients are written straight into the flat ``grad`` arena by ``arena_linear``;
+  every other gradient (convolutions, normalisation layers: cuDNN allocates its own output) is
+  left where autograd put it and handed to the kernels through a segment table
+  (``multi_tensor.GradSegTable``): on one GPU the fused update reads it in place
+  (``frl_*_mt``: no flatten pass at all), with several GPUs ONE ``frl_flatten_grads`` launch per
+  bucket gathers the bucket's stragglers into the slice NCCL / the NVLS kernel reduce **in place**
+  — no per-tensor copy kernels, no copy-out;
 * the 1/world mean and the clip coefficient are folded into the update kernel's gradient read;
 * each bucket's all-reduce is issued on a side stream the moment its last gradient is ready and
   its fused update is chained right behind it, overlapping the rest of backward;
 * with clipping enabled the updates wait for the global norm (two-phase tail), computed by one
   reduction kernel over the model range with no host sync.
 """
-from typing import Callable, List, Optional, Tuple
+import os
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -25,6 +29,31 @@ from .arena import ParamArena
 from .fused_optim import FusedArenaOptimizer
 
 KERNELS = _native     # swapped by CPU tests of the host logic
+
+
+class _TableSet:
+    """Segment tables of one pipeline, built on first use: the whole arena (1-GPU tail update that
+    reads gradients in place) and, per (bucket, set of straggler slots), the flatten tables.
+    A CUDA-graph capture gets a set of its own: captured uploads read the set's pinned rows at
+    every replay, so nothing else may ever rewrite them."""
+
+    def __init__(self, arena) -> None:
+        self.arena = arena
+        self._whole = None
+        self._flatten: Dict[Tuple, object] = {}
+
+    def whole(self):
+        if self._whole is None:
+            from .multi_tensor import GradSegTable
+            self._whole = GradSegTable(self.arena.slots, self.arena.device)
+        return self._whole
+
+    def flatten(self, key, slots):
+        t = self._flatten.get(key)
+        if t is None:
+            from .multi_tensor import GradSegTable
+            t = self._flatten[key] = GradSegTable(slots, self.arena.device)
+        return t
 
 
 class _Bucket:
@@ -110,6 +139,13 @@ class GradBucketPipeline:
         self.slot_states = {}
         self.forward_gen = 0
         self._deferred = {}
+        # gradients autograd allocated itself, by slot index, kept alive until the kernels that
+        # read them in place have been enqueued (multi-tensor path; CUDA only)
+        self.mt_enabled = (self.on_cuda and hasattr(KERNELS, "flatten_grads")
+                           and os.environ.get("FRL_B200_MT_GRADS", "1") != "0")
+        self._ext: Dict[int, torch.Tensor] = {}
+        self.tables = _TableSet(arena)
+        self._keep_ext = False       # replay of a captured step: the capture owns the references
         # timing taps (bench): list of (start_event, end_event, lo, hi) for update launches
         self.record_update_events = False
         self.update_events: List[Tuple[torch.cuda.Event, torch.cuda.Event, int, int]] = []
@@ -133,15 +169,59 @@ class GradBucketPipeline:
         return self._step_open
 
     def _make_hook(self, slot) -> Callable[[nn.Parameter], None]:
+        from .multi_tensor import grad_usable_in_place
+
         def hook(param: nn.Parameter) -> None:
             g = param.grad
             if g is not None:
                 dst = self.arena.grad_view(slot)
                 if g.data_ptr() != dst.data_ptr():
-                    dst.copy_(g)              # flatten (casts fp32 -> bf16 grads when needed)
+                    if self.mt_enabled and self._step_open and grad_usable_in_place(g, slot):
+                        self._ext[slot.index] = g     # read in place / gathered per bucket later
+                    else:
+                        dst.copy_(g)          # odd layouts, CPU tensors: flatten this one now
                 param.grad = None             # next backward steals again instead of accumulating
             self.mark_ready(slot)
         return hook
+
+    # -- multi-tensor plumbing ---------------------------------------------------------------------
+    def _point(self, table) -> None:
+        """This step's gradient locations into ``table`` (arena slice unless a straggler)."""
+        g_arena = self.arena.grad
+        esz = g_arena.element_size()
+        base = g_arena.data_ptr()
+        for s in table.slots:
+            g = self._ext.get(s.index)
+            if g is None:
+                table.point(s, base + s.offset * esz, g_arena.dtype)
+            else:
+                table.point(s, g.data_ptr(), g.dtype)
+
+    def _flatten_stragglers(self, slots, key, side: bool) -> None:
+        """ONE launch: gather the listed slots' out-of-arena gradients into their arena slices
+        (cast to the arena's gradient dtype) on the current stream."""
+        ext = [s for s in slots if s.index in self._ext]
+        if not ext:
+            return
+        table = self.tables.flatten((key, tuple(s.index for s in ext)), ext)
+        self._point(table)
+        table.upload()
+        KERNELS.flatten_grads(table, self.arena.grad, scale=1.0)
+        for s in ext:
+            g = self._ext.pop(s.index) if not self._keep_ext else self._ext[s.index]
+            if side:
+                g.record_stream(torch.cuda.current_stream())
+
+    def materialize_grads(self) -> None:
+        """Debug/inspection aid: make ``arena.grad`` hold every gradient of the open step."""
+        self._flatten_stragglers(self.arena.slots, "all", side=False)
+
+    def detach_grad_refs(self):
+        """Hand the straggler references and the table set to a captured graph (which replays
+        kernels that read exactly these addresses); the pipeline continues with fresh ones."""
+        refs, tables = self._ext, self.tables
+        self._ext, self.tables = {}, _TableSet(self.arena)
+        return refs, tables
 
     def mark_ready(self, slot) -> None:
         if not self._step_open or id(slot.param) in self._ready_ids:
@@ -167,6 +247,8 @@ class GradBucketPipeline:
             self.side_stream.wait_stream(cur)
             torch.cuda.set_stream(self.side_stream)
         try:
+            if self._ext:
+                self._flatten_stragglers(b.slots, id(b), side=self.on_cuda)
             if self.nvls is not None and not b.replicated:
                 self._update(b.lo, b.hi, None)        # K7: reduce + update + broadcast
             elif self.distributed:
@@ -221,6 +303,7 @@ class GradBucketPipeline:
                     f"indices {missing} did not receive a gradient in this step")
             if self.eager and self.on_cuda:
                 torch.cuda.current_stream().wait_stream(self.side_stream)
+            self._flatten_stragglers(self.arena.slots, "all", side=False)
             self._finish_partial(missing)
             return
         if self.distributed or self.eager:
@@ -245,6 +328,7 @@ class GradBucketPipeline:
                 self._tail_deferred = True
                 return
             self._tail_update()
+        self._ext.clear()
         self.optimizer.end_step()
 
     @property
@@ -252,22 +336,52 @@ class GradBucketPipeline:
         """True if a step ends with tail launches (not everything is updated eagerly)."""
         return not self.eager
 
-    def run_tail(self) -> None:
+    def run_tail(self, grad_refs=None, tables=None) -> None:
         """The deferred part of ``finish_step(defer_tail=True)``; also what a CUDA-graph replay
-        of the captured step is followed by."""
-        if self.has_tail:
-            self._tail_update()
+        of the captured step is followed by (then with the capture's gradient references and
+        segment tables: the replayed backward wrote to exactly those addresses)."""
+        if grad_refs is not None:
+            mine = (self._ext, self.tables)
+            self._ext, self.tables, self._keep_ext = grad_refs, tables, True
+        try:
+            if self.has_tail:
+                self._tail_update()
+        finally:
+            if grad_refs is not None:
+                (self._ext, self.tables), self._keep_ext = mine, False
         self.optimizer.end_step()
 
     def _tail_update(self) -> None:
         coef = None
         if self.clip_norm > 0.0:
+            # the global norm needs every gradient first: gather the stragglers, then K3 + K2
+            self._flatten_stragglers(self.arena.slots, "all", side=False)
             n_model = self.arena.model_end
             KERNELS.grad_sumsq_clip(self.arena.grad[:n_model], n_model, pre_scale=self.grad_scale,
                                     max_norm=self.clip_norm, out3=self.clip_out,
                                     scratch=self.clip_scratch)
             coef = self.clip_out[2:3]
+        if self._ext and not self.distributed:
+            # one GPU: the update reads every gradient where it lies — no flatten pass
+            table = self.tables.whole()
+            self._point(table)
+            table.upload()
+            self._update_table(table)
+            if not self._keep_ext:
+                self._ext.clear()
+            return
         self._update(0, self.arena.numel, coef)
+
+    def _update_table(self, table) -> None:
+        if self.record_update_events and self.on_cuda:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.optimizer.apply_table(table, grad_scale=self.grad_scale)
+            e1.record()
+            self.update_events.append((e0, e1, 0, self.arena.numel))
+        else:
+            self.optimizer.apply_table(table, grad_scale=self.grad_scale)
 
     def _finish_partial(self, missing) -> None:
         """world_size == 1 and some parameters got no gradient: torch.optim skips those (no

@@ -106,6 +106,10 @@ class _Captured:
             w.pipeline.begin_step()
             total.backward()
             w.pipeline.finish_step(defer_tail=True)
+        # gradients autograd allocated inside the capture (conv / norm layers) and the segment
+        # tables that name them now belong to this graph: the replayed backward writes to exactly
+        # those addresses, the tail update / the captured flatten launches read them there
+        self.grad_refs, self.tables = w.pipeline.detach_grad_refs()
         # capture executed nothing on the device, but begin_step() counted a step: undo it, the
         # replay performs the step for real (finish_step(defer_tail=True) left the optimizer's
         # step counter to run_tail())
@@ -138,7 +142,7 @@ class _Captured:
         global REPLAYED_LAUNCHES
         REPLAYED_LAUNCHES += self.frl_kernels
         w.pipeline.step_id += 1
-        w.pipeline.run_tail()                 # tail update (1 GPU / clipping) + step counter
+        w.pipeline.run_tail(self.grad_refs, self.tables)   # tail update (1 GPU / clipping) + step counter
         if sink_row is not None:
             row = self._loss_vec
             if row is None:

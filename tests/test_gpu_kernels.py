@@ -546,3 +546,108 @@ def test_fused_linear_relu_units_match_the_unfused_modules(precision, monkeypatc
         torch.testing.assert_close(a, b, **tol)
     torch.testing.assert_close(results[1][0], results[0][0], **tol)
     torch.testing.assert_close(results[1][1], results[0][1], **tol)
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 / K2-mt — multi-tensor forms: gradients read where autograd left them (segment tables)
+# ------------------------------------------------------------------------------------------------
+
+class _Slot:
+    def __init__(self, index, offset, numel):
+        self.index, self.offset, self.numel = index, offset, numel
+
+
+def _mt_case(seed=0, sizes=(10, 64, 3, 9408, 4097, 8, 1, 36864, 4096 * 5 + 2, 1000)):
+    """Slots at 8-aligned arena offsets (arena.py layout) + one separately allocated gradient
+    tensor per slot, fp32 and bf16 mixed as in a BF16-mode run with criterion parameters."""
+    from frl_b200.multi_tensor import GradSegTable
+    rs = np.random.RandomState(seed)
+    slots, off = [], 0
+    for i, n in enumerate(sizes):
+        slots.append(_Slot(i, off, n))
+        off = (off + n + 7) // 8 * 8
+    grads = []
+    for i, s in enumerate(slots):
+        g = _dev(rs.randn(s.numel).astype(np.float32), torch.bfloat16 if i % 3 == 1 else torch.float32)
+        grads.append(g)
+    table = GradSegTable(slots, torch.device(DEV))
+    for s, g in zip(slots, grads):
+        table.point(s, g.data_ptr(), g.dtype)
+    table.upload()
+    return slots, grads, table, off
+
+
+@pytest.mark.parametrize("dst", [torch.float32, torch.bfloat16])
+def test_flatten_grads_gathers_every_segment_in_one_launch(dst):
+    slots, grads, table, n = _mt_case()
+    arena = torch.full((n,), 7.0, dtype=dst, device=DEV)
+    before = _native.launch_count()
+    _native.flatten_grads(table, arena, scale=0.5)
+    assert _native.launch_count() - before == 1
+    torch.cuda.synchronize()
+    for s, g in zip(slots, grads):
+        want = (g.float() * 0.5).to(dst)
+        assert torch.equal(arena[s.offset:s.offset + s.numel], want), s.index
+        # the padding up to the next multiple of 4 is zero-filled, the rest of the gap untouched
+        pad4 = (s.numel + 3) // 4 * 4
+        assert torch.all(arena[s.offset + s.numel:s.offset + pad4] == 0)
+    # pointing the same table at other tensors and uploading again is enough for the next step
+    grads2 = [torch.ones_like(g) for g in grads]
+    for s, g in zip(slots, grads2):
+        table.point(s, g.data_ptr(), g.dtype)
+    table.upload()
+    _native.flatten_grads(table, arena, scale=1.0)
+    torch.cuda.synchronize()
+    assert all(torch.all(arena[s.offset:s.offset + s.numel] == 1) for s in slots)
+
+
+@pytest.mark.parametrize("algo", ["sgd", "adam", "adam_amsgrad", "rmsprop"])
+@pytest.mark.parametrize("lp", [False, True])
+def test_multi_tensor_update_equals_flatten_then_flat_update(algo, lp):
+    """K2-mt reads the gradients in place; the result must be BIT-identical to gathering them into
+    the arena (fp32, so no rounding on the way) and running the flat K2 over it."""
+    slots, grads, table, n = _mt_case(seed=3)
+    rs = np.random.RandomState(9)
+    p0 = rs.randn(n).astype(np.float32)
+    used = np.zeros(n, bool)
+    for s in slots:
+        used[s.offset:s.offset + s.numel] = True
+    p0[~used] = 0.0                                   # arena padding is zero
+    flat_g = torch.zeros(n, device=DEV)
+    _native.flatten_grads(table, flat_g, scale=1.0)
+
+    def run(mt):
+        p = _dev(p0)
+        s0, s1, s2 = (torch.zeros(n, device=DEV) for _ in range(3))
+        p_lp = torch.zeros(n, dtype=torch.bfloat16, device=DEV) if lp else None
+        for step in range(3):
+            first = step == 0
+            if algo == "sgd":
+                if mt:
+                    _native.sgd_momentum_mt(p, s0, p_lp, table, lr=0.05, mu=0.9, dampening=0.0, wd=1e-5,
+                                            grad_scale=0.5, first_step=first)
+                else:
+                    _native.sgd_momentum(p, flat_g, s0, p_lp, n, lr=0.05, mu=0.9, dampening=0.0, wd=1e-5,
+                                         grad_scale=0.5, first_step=first)
+            elif algo.startswith("adam"):
+                vmax = s2 if algo == "adam_amsgrad" else None
+                kw = dict(lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8, wd=1e-5, step=step + 1, grad_scale=0.5)
+                if mt:
+                    _native.adam_mt(p, s0, s1, vmax, p_lp, table, **kw)
+                else:
+                    _native.adam(p, flat_g, s0, s1, vmax, p_lp, n, **kw)
+            else:
+                kw = dict(lr=1e-2, alpha=0.99, eps=1e-8, wd=1e-5, mu=0.9, grad_scale=0.5)
+                if mt:
+                    _native.rmsprop_mt(p, s0, s1, p_lp, table, **kw)
+                else:
+                    _native.rmsprop(p, flat_g, s0, s1, p_lp, n, **kw)
+        torch.cuda.synchronize()
+        return p, s0, s1, s2, p_lp
+
+    a, b = run(True), run(False)
+    for s in slots:
+        sl = slice(s.offset, s.offset + s.numel)
+        for x, y in zip(a, b):
+            if x is not None:
+                assert torch.equal(x[sl], y[sl]), (algo, s.index)
