@@ -56,10 +56,10 @@ SIGNATURES = {
     "frl_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i64, _d, _vp, _vp, _i, _vp]),
     "frl_rmsprop": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _d, _vp, _vp, _i, _vp]),
     "frl_mt_tile_elems": (_i64, []),
-    "frl_flatten_grads": (_i, [_vp, _vp, _i, _i64, _vp, _i, _d, _vp]),
-    "frl_sgd_momentum_mt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _d, _d, _d, _d, _d, _vp, _vp, _i, _vp]),
-    "frl_adam_mt": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _d, _d, _d, _d, _d, _i64, _d, _vp, _vp, _vp]),
-    "frl_rmsprop_mt": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _d, _d, _d, _d, _d, _d, _vp, _vp, _vp]),
+    "frl_flatten_grads": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _d, _vp]),
+    "frl_sgd_momentum_mt": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _vp, _vp, _i, _vp]),
+    "frl_adam_mt": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i64, _d, _vp, _vp, _vp]),
+    "frl_rmsprop_mt": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _d, _vp, _vp, _vp]),
     "frl_reduce_scratch_bytes": (_i64, []),
     "frl_grad_sumsq_clip": (_i, [_vp, _i64, _i, _f, _f, _vp, _vp, _vp]),
     "frl_criteria_scratch_bytes": (_i64, [_i]),
@@ -185,7 +185,7 @@ def mt_tile_elems() -> int:
 def flatten_grads(table, arena_grad, *, scale: float = 1.0) -> None:
     """arena_grad[seg.arena_off + i] = cast(seg.g[i] * scale) for every segment of ``table``
     (a ``multi_tensor.GradSegTable`` whose device copy is current): one launch."""
-    _check(lib().frl_flatten_grads(table.segs_dev_ptr, table.prefix_dev_ptr, table.n_segs, table.n_tiles,
+    _check(lib().frl_flatten_grads(table.segs_dev_ptr, table.prefix_dev_ptr, table.tile_seg_dev_ptr, table.n_tiles,
                                    _ptr(arena_grad), dtype_code(arena_grad.dtype), scale, _stream()),
            "frl_flatten_grads")
 
@@ -193,7 +193,7 @@ def flatten_grads(table, arena_grad, *, scale: float = 1.0) -> None:
 def sgd_momentum_mt(p, buf, p_lp, table, *, lr, mu, dampening, wd, grad_scale=1.0, grad_scale_dev=None,
                     first_step=False, dyn=None) -> None:
     _check(lib().frl_sgd_momentum_mt(_ptr(p), _ptr(buf), _ptr(p_lp), table.segs_dev_ptr, table.prefix_dev_ptr,
-                                     table.n_segs, table.n_tiles, lr, mu, dampening, wd, grad_scale,
+                                     table.tile_seg_dev_ptr, table.n_tiles, lr, mu, dampening, wd, grad_scale,
                                      _ptr(grad_scale_dev), _ptr(dyn), int(first_step), _stream()),
            "frl_sgd_momentum_mt")
 
@@ -201,14 +201,14 @@ def sgd_momentum_mt(p, buf, p_lp, table, *, lr, mu, dampening, wd, grad_scale=1.
 def adam_mt(p, m, v, vmax, p_lp, table, *, lr, beta1, beta2, eps, wd, step, grad_scale=1.0,
             grad_scale_dev=None, dyn=None) -> None:
     _check(lib().frl_adam_mt(_ptr(p), _ptr(m), _ptr(v), _ptr(vmax), _ptr(p_lp), table.segs_dev_ptr,
-                             table.prefix_dev_ptr, table.n_segs, table.n_tiles, lr, beta1, beta2, eps, wd,
+                             table.prefix_dev_ptr, table.tile_seg_dev_ptr, table.n_tiles, lr, beta1, beta2, eps, wd,
                              step, grad_scale, _ptr(grad_scale_dev), _ptr(dyn), _stream()), "frl_adam_mt")
 
 
 def rmsprop_mt(p, sq, buf, p_lp, table, *, lr, alpha, eps, wd, mu, grad_scale=1.0, grad_scale_dev=None,
                dyn=None) -> None:
     _check(lib().frl_rmsprop_mt(_ptr(p), _ptr(sq), _ptr(buf), _ptr(p_lp), table.segs_dev_ptr,
-                                table.prefix_dev_ptr, table.n_segs, table.n_tiles, lr, alpha, eps, wd, mu,
+                                table.prefix_dev_ptr, table.tile_seg_dev_ptr, table.n_tiles, lr, alpha, eps, wd, mu,
                                 grad_scale, _ptr(grad_scale_dev), _ptr(dyn), _stream()), "frl_rmsprop_mt")
 
 

@@ -147,14 +147,22 @@ class ParamArena:
 
     # -- export --------------------------------------------------------------------------------
     @contextmanager
-    def exported(self, cpu: bool = True):
+    def exported(self, cpu: bool = True, module: Optional[nn.Module] = None):
         """Temporarily give every parameter a private fp32 copy of its master weights.
 
         Inside the block the module pickles / ``state_dict``s exactly like an un-wrapped fp32
         module (what the reference's checkpoint files hold, reference solver.py:632-651).
+        ``module``: also present its reduced-precision floating buffers (BatchNorm statistics,
+        where a BF16-mode run had to keep them in bf16) as fp32 for the duration.
         """
         saved = []
+        saved_bufs = []
         try:
+            if module is not None:
+                for buf in module.buffers():
+                    if buf.is_floating_point() and buf.dtype != torch.float32:
+                        saved_bufs.append((buf, buf.data))
+                        buf.data = buf.data.float()
             for s in self.slots:
                 saved.append((s.param, s.param.data, s.param.grad))
                 clone = self.master_view(s).detach().clone()
@@ -165,6 +173,8 @@ class ParamArena:
             for p, data, grad in saved:
                 p.data = data
                 p.grad = grad
+            for buf, data in saved_bufs:
+                buf.data = data
 
     def buckets(self, cap_bytes: int, first_cap_bytes: Optional[int] = None
                 ) -> List[Tuple[int, int]]:

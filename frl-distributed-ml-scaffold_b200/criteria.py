@@ -219,6 +219,23 @@ class _FusedLosses(torch.autograd.Function):
         return (None, None, *douts)
 
 
+_path_logged = set()
+
+
+def _log_path_once(modules, fused: bool) -> None:
+    """One line per distinct set of loss modules: did the fused kernels take them, or does the
+    user's plugin code run as composed torch ops (the reference's own path)."""
+    key = (tuple(type(m).__name__ for m in modules), fused)
+    if key not in _path_logged:
+        _path_logged.add(key)
+        import logging
+        logging.getLogger(__name__).info(
+            "criterion path for loss modules %s: %s", list(key[0]),
+            "fused kernels (frl_criteria_forward / _backward, one launch each)" if fused else
+            "composed torch ops — outside the fused kernels' domain (MSE / CrossEntropy with mean "
+            "reduction, optionally inside MaskedLoss)")
+
+
 def fused_task_losses(modules, outputs, targets, weights=None, sink=None, nan_flag=None
                       ) -> Optional[torch.Tensor]:
     """[total, L_1..L_T] through the fused kernels, or None if the tasks are outside their
@@ -226,6 +243,7 @@ def fused_task_losses(modules, outputs, targets, weights=None, sink=None, nan_fl
     if not outputs or not outputs[0].is_cuda:
         return None
     plan = _plan_for(modules, outputs, targets, weights)
+    _log_path_once(modules, plan is not None)
     if plan is None:
         return None
     plan.sink = sink

@@ -9,6 +9,8 @@
 // single 16-byte (bf16) / two 16-byte (fp32) loads per lane, rows strided across the warps and
 // row splits; per-CTA partials go to scratch and the last CTA of each column tile (atomic
 // ticket) folds the splits in a fixed order — deterministic, no float atomics.
+#include <stdlib.h>
+
 #include "frl_common.cuh"
 
 namespace frl {
@@ -16,8 +18,8 @@ namespace frl {
 constexpr int kSThreads = 256;
 constexpr int kSWarps = kSThreads / 32;
 constexpr int kSCols = 32 * 8;          // columns per CTA tile
-constexpr int kSMaxSplits = 64;
-constexpr int kSRowsInFlight = 4;
+constexpr int kSMaxSplits = 128;
+
 
 struct ColsumScratchHeader { unsigned int ticket[1]; };
 
@@ -53,7 +55,7 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
 // MASK (K6b): x is dY of a ReLU layer, `act` its forward output; dZ = act > 0 ? dY : 0 is written
 // to `dz` on the way and the column sums are those of dZ — ReLU's backward and the bias-gradient
 // reduction in the one pass over dY that the reduction needs anyway.
-template <typename XT, typename OT, bool VEC, bool MASK>
+template <typename XT, typename OT, bool VEC, bool MASK, int kSRowsInFlight>
 __global__ void __launch_bounds__(kSThreads)
 colsum_kernel(const XT* __restrict__ x, const XT* __restrict__ act, XT* __restrict__ dz, int64_t rows,
               int64_t cols, OT* __restrict__ out,
@@ -140,7 +142,12 @@ colsum_kernel(const XT* __restrict__ x, const XT* __restrict__ act, XT* __restri
 
 static inline int64_t colsum_tiles(int64_t cols) { return (cols + kSCols - 1) / kSCols; }
 static inline int colsum_splits(int64_t rows, int64_t tiles) {
-    int64_t want = (static_cast<int64_t>(sm_count()) * 4 + tiles - 1) / tiles;    // ~4 CTAs per SM
+    static const int ctas_per_sm = [] {
+        const char* e = getenv("FRL_B200_COLSUM_CTAS");        // tuning knob
+        const int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : v;
+    }();
+    int64_t want = (static_cast<int64_t>(sm_count()) * ctas_per_sm + tiles - 1) / tiles;
     const int64_t max_by_rows = (rows + kSWarps - 1) / kSWarps;
     if (want > max_by_rows) want = max_by_rows;
     if (want > kSMaxSplits) want = kSMaxSplits;
@@ -173,12 +180,22 @@ static int launch_colsum(const void* x, const void* act, void* dz, int x_dtype, 
     float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +
                                               ((tiles * sizeof(unsigned int) + 15) / 16) * 16);
     const bool vec = (cols % 8 == 0) && aligned16(x) && (!mask || (aligned16(act) && aligned16(dz)));
+    static const int rows_in_flight = [] {
+        const char* e = getenv("FRL_B200_COLSUM_ROWS");       // tuning knob: rows a warp keeps in flight
+        return e ? atoi(e) : 1;
+    }();
     dim3 grid(static_cast<unsigned int>(tiles), static_cast<unsigned int>(splits));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define FRL_CS2(XT, OT, V, M)                                                                        \
-    colsum_kernel<XT, OT, V, M><<<grid, kSThreads, 0, st>>>(                                         \
+#define FRL_CS3(XT, OT, V, M, R)                                                                     \
+    colsum_kernel<XT, OT, V, M, R><<<grid, kSThreads, 0, st>>>(                                      \
         static_cast<const XT*>(x), static_cast<const XT*>(act), static_cast<XT*>(dz), rows, cols,    \
         static_cast<OT*>(out), accumulate, tickets, partial)
+#define FRL_CS2(XT, OT, V, M)                                                                        \
+    do {                                                                                             \
+        if (rows_in_flight >= 4) FRL_CS3(XT, OT, V, M, 4);                                           \
+        else if (rows_in_flight == 2) FRL_CS3(XT, OT, V, M, 2);                                      \
+        else FRL_CS3(XT, OT, V, M, 1);                                                               \
+    } while (0)
 #define FRL_CS(XT, OT)                                                                               \
     do {                                                                                             \
         if (vec && mask) FRL_CS2(XT, OT, true, true);                                                \
@@ -192,6 +209,7 @@ static int launch_colsum(const void* x, const void* act, void* dz, int x_dtype, 
     else FRL_CS(float, __nv_bfloat16);
 #undef FRL_CS
 #undef FRL_CS2
+#undef FRL_CS3
     return after_launch(name);
 }
 

@@ -170,8 +170,9 @@ static int launch_update(const Rule& rule, float* p, const void* g, float* s0, f
 //                       NCCL / the NVLS kernel reduce (world > 1: copy-in only, cast and pre-scale
 //                       folded in, no copy-out, no per-tensor launches).
 // Work is cut into tiles of kTileElems arena elements that never straddle a segment;
-// tile_prefix[s] = first tile of segment s (n_segs + 1 entries).  A CTA finds its segment by
-// binary search in that (L1-resident, <= 2 KB) array: ~8 probes per 16 KB+ of streamed data.
+// tile_prefix[s] = first tile of segment s (n_segs + 1 entries), tile_seg[t] = segment of tile t
+// (both built once on the host: sizes never change).  Interior tiles run the flat kernel's body;
+// only the last tile of a tensor is bounds-checked.
 constexpr int kTileElems = kTileVec * 4;
 
 struct SegView {
@@ -181,20 +182,18 @@ struct SegView {
     int64_t t_in;      // tile index inside the segment
 };
 
+// tile -> segment through a per-tile int32 map built once on the host (sizes never change): one
+// L2-resident 4-byte read per 16 KB+ of streamed data
 __device__ __forceinline__ SegView find_segment(const frl_grad_seg* __restrict__ segs,
-                                                const int64_t* __restrict__ tile_prefix, int n_segs,
-                                                int64_t tile) {
-    int lo = 0, hi = n_segs;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(tile_prefix + mid) <= tile) lo = mid; else hi = mid;
-    }
+                                                const int64_t* __restrict__ tile_prefix,
+                                                const int32_t* __restrict__ tile_seg, int64_t tile) {
+    const int si = __ldg(tile_seg + tile);
     SegView v;
-    v.g = segs[lo].g;
-    v.arena_off = segs[lo].arena_off;
-    v.numel = segs[lo].numel;
-    v.g_dtype = segs[lo].g_dtype;
-    v.t_in = tile - __ldg(tile_prefix + lo);
+    v.g = segs[si].g;
+    v.arena_off = segs[si].arena_off;
+    v.numel = segs[si].numel;
+    v.g_dtype = segs[si].g_dtype;
+    v.t_in = tile - __ldg(tile_prefix + si);
     return v;
 }
 
@@ -214,12 +213,39 @@ __device__ __forceinline__ f32x4 seg_load4(const SegView& sv, int64_t e) {
     return f32x4{t[0], t[1], t[2], t[3]};
 }
 
+// interior tile (every vector of the tile lies inside the gradient tensor): the flat kernel's body
+template <typename Rule, typename GVec, int NS, bool HAS_LP>
+__device__ __forceinline__ void mt_full_tile(const Rule& rule, float gs, f32x4* p, f32x4* s0, f32x4* s1,
+                                             f32x4* s2, bf16x4* lp, const GVec* g, int64_t a0, int64_t v0) {
+    const f32x4 zero{0.f, 0.f, 0.f, 0.f};
+    f32x4 vp[kUnroll], vg[kUnroll], a_0[kUnroll], a_1[kUnroll], a_2[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t v = v0 + j * kThreads, i = a0 + v;
+        vg[j] = load_grad4(g, v);
+        vp[j] = ld_stream(p + i);
+        a_0[j] = NS > 0 ? ld_stream(s0 + i) : zero;
+        a_1[j] = NS > 1 ? ld_stream(s1 + i) : zero;
+        a_2[j] = NS > 2 ? ld_stream(s2 + i) : zero;
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = a0 + v0 + j * kThreads;
+        apply4(rule, vp[j], vg[j], gs, a_0[j], a_1[j], a_2[j]);
+        st_stream(p + i, vp[j]);
+        if (NS > 0) st_stream(s0 + i, a_0[j]);
+        if (NS > 1) st_stream(s1 + i, a_1[j]);
+        if (NS > 2) st_stream(s2 + i, a_2[j]);
+        if (HAS_LP) st_stream(lp + i, bf16x4{pack_bf16(vp[j].x, vp[j].y), pack_bf16(vp[j].z, vp[j].w)});
+    }
+}
+
 template <typename Rule, int NS, bool HAS_LP>
 __global__ void __launch_bounds__(kThreads)
 update_mt_kernel(float* __restrict__ p_, float* __restrict__ s0_, float* __restrict__ s1_,
                  float* __restrict__ s2_, bf16x4* __restrict__ lp,
                  const frl_grad_seg* __restrict__ segs, const int64_t* __restrict__ tile_prefix,
-                 int n_segs, int64_t n_tiles, Rule rule, float gscale,
+                 const int32_t* __restrict__ tile_seg, int64_t n_tiles, Rule rule, float gscale,
                  const float* __restrict__ gscale_dev, const float* __restrict__ dyn) {
     if (dyn) rule.patch(dyn);
     f32x4* p = reinterpret_cast<f32x4*>(p_);
@@ -229,34 +255,35 @@ update_mt_kernel(float* __restrict__ p_, float* __restrict__ s0_, float* __restr
     const float gs = gscale_dev ? gscale * __ldg(gscale_dev) : gscale;
     const f32x4 zero{0.f, 0.f, 0.f, 0.f};
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const SegView sv = find_segment(segs, tile_prefix, n_segs, tile);
-        const int64_t seg_vec = (sv.numel + 3) >> 2;              // arena slices are padded to 8
+        const SegView sv = find_segment(segs, tile_prefix, tile_seg, tile);
         const int64_t v0 = sv.t_in * kTileVec + threadIdx.x;      // vec4 index inside the segment
         const int64_t a0 = sv.arena_off >> 2;                     // vec4 index of the segment in the arena
-        f32x4 vp[kUnroll], vg[kUnroll], a_0[kUnroll], a_1[kUnroll], a_2[kUnroll];
-#pragma unroll
-        for (int j = 0; j < kUnroll; ++j) {
-            const int64_t v = v0 + j * kThreads;
-            if (v < seg_vec) {
-                const int64_t i = a0 + v;
-                vg[j] = seg_load4(sv, v << 2);
-                vp[j] = ld_stream(p + i);
-                a_0[j] = NS > 0 ? ld_stream(s0 + i) : zero;
-                a_1[j] = NS > 1 ? ld_stream(s1 + i) : zero;
-                a_2[j] = NS > 2 ? ld_stream(s2 + i) : zero;
-            }
+        if ((sv.t_in + 1) * kTileVec <= (sv.numel >> 2)) {        // CTA-uniform: interior tile
+            if (sv.g_dtype == FRL_F32)
+                mt_full_tile<Rule, f32x4, NS, HAS_LP>(rule, gs, p, s0, s1, s2, lp,
+                                                      static_cast<const f32x4*>(sv.g), a0, v0);
+            else
+                mt_full_tile<Rule, bf16x4, NS, HAS_LP>(rule, gs, p, s0, s1, s2, lp,
+                                                       static_cast<const bf16x4*>(sv.g), a0, v0);
+            continue;
         }
-#pragma unroll
+        // last tile of a segment (or a small tensor): bounds-checked, element-wise at the very end
+        const int64_t seg_vec = (sv.numel + 3) >> 2;              // arena slices are padded to 8
+#pragma unroll 1
         for (int j = 0; j < kUnroll; ++j) {
             const int64_t v = v0 + j * kThreads;
             if (v >= seg_vec) break;
             const int64_t i = a0 + v;
-            apply4(rule, vp[j], vg[j], gs, a_0[j], a_1[j], a_2[j]);
-            st_stream(p + i, vp[j]);
-            if (NS > 0) st_stream(s0 + i, a_0[j]);
-            if (NS > 1) st_stream(s1 + i, a_1[j]);
-            if (NS > 2) st_stream(s2 + i, a_2[j]);
-            if (HAS_LP) st_stream(lp + i, bf16x4{pack_bf16(vp[j].x, vp[j].y), pack_bf16(vp[j].z, vp[j].w)});
+            f32x4 qg = seg_load4(sv, v << 2), qp = ld_stream(p + i);
+            f32x4 q0 = NS > 0 ? ld_stream(s0 + i) : zero;
+            f32x4 q1 = NS > 1 ? ld_stream(s1 + i) : zero;
+            f32x4 q2 = NS > 2 ? ld_stream(s2 + i) : zero;
+            apply4(rule, qp, qg, gs, q0, q1, q2);
+            st_stream(p + i, qp);
+            if (NS > 0) st_stream(s0 + i, q0);
+            if (NS > 1) st_stream(s1 + i, q1);
+            if (NS > 2) st_stream(s2 + i, q2);
+            if (HAS_LP) st_stream(lp + i, bf16x4{pack_bf16(qp.x, qp.y), pack_bf16(qp.z, qp.w)});
         }
     }
 }
@@ -273,9 +300,10 @@ template <> __device__ __forceinline__ void store_flat4<bf16x4>(bf16x4* dst, int
 template <typename DVec>
 __global__ void __launch_bounds__(kThreads)
 flatten_kernel(DVec* __restrict__ dst, const frl_grad_seg* __restrict__ segs,
-               const int64_t* __restrict__ tile_prefix, int n_segs, int64_t n_tiles, float scale) {
+               const int64_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_seg,
+               int64_t n_tiles, float scale) {
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const SegView sv = find_segment(segs, tile_prefix, n_segs, tile);
+        const SegView sv = find_segment(segs, tile_prefix, tile_seg, tile);
         const int64_t seg_vec = (sv.numel + 3) >> 2;
         const int64_t v0 = sv.t_in * kTileVec + threadIdx.x;
         const int64_t a0 = sv.arena_off >> 2;
@@ -311,21 +339,21 @@ static int grid_for_tiles(K kernel, int64_t n_tiles) {
 
 template <typename Rule, int NS>
 static int launch_update_mt(const Rule& rule, float* p, float* s0, float* s1, float* s2, void* p_lp,
-                            const frl_grad_seg* segs, const int64_t* tile_prefix, int n_segs,
+                            const frl_grad_seg* segs, const int64_t* tile_prefix, const int32_t* tile_seg,
                             int64_t n_tiles, float gscale, const float* gscale_dev, const float* dyn,
                             cudaStream_t st, const char* name) {
-    FRL_REQUIRE(n_segs >= 0 && n_tiles >= 0, FRL_E_ARG, "%s: negative counts", name);
-    if (n_segs == 0 || n_tiles == 0) return 0;
-    FRL_REQUIRE(p && segs && tile_prefix, FRL_E_ARG, "%s: null p/segs/tile_prefix", name);
+    FRL_REQUIRE(n_tiles >= 0, FRL_E_ARG, "%s: negative tile count", name);
+    if (n_tiles == 0) return 0;
+    FRL_REQUIRE(p && segs && tile_prefix && tile_seg, FRL_E_ARG, "%s: null p/segs/tile_prefix/tile_seg", name);
     FRL_REQUIRE(aligned16(p) && aligned16(s0) && aligned16(s1) && aligned16(s2) && aligned16(p_lp),
                 FRL_E_ALIGN, "%s: arrays must be 16-byte aligned", name);
     bf16x4* lp = static_cast<bf16x4*>(p_lp);
     if (lp)
         update_mt_kernel<Rule, NS, true><<<grid_for_tiles(update_mt_kernel<Rule, NS, true>, n_tiles), kThreads, 0, st>>>(
-            p, s0, s1, s2, lp, segs, tile_prefix, n_segs, n_tiles, rule, gscale, gscale_dev, dyn);
+            p, s0, s1, s2, lp, segs, tile_prefix, tile_seg, n_tiles, rule, gscale, gscale_dev, dyn);
     else
         update_mt_kernel<Rule, NS, false><<<grid_for_tiles(update_mt_kernel<Rule, NS, false>, n_tiles), kThreads, 0, st>>>(
-            p, s0, s1, s2, lp, segs, tile_prefix, n_segs, n_tiles, rule, gscale, gscale_dev, dyn);
+            p, s0, s1, s2, lp, segs, tile_prefix, tile_seg, n_tiles, rule, gscale, gscale_dev, dyn);
     return after_launch(name);
 }
 
@@ -400,26 +428,27 @@ extern "C" int frl_rmsprop(float* p, const void* g, float* sq, float* buf, void*
 
 extern "C" int64_t frl_mt_tile_elems(void) { return kTileElems; }
 
-extern "C" int frl_flatten_grads(const frl_grad_seg* segs_dev, const int64_t* tile_prefix_dev, int n_segs,
-                                 int64_t n_tiles, void* arena_grad, int dst_dtype, double scale, void* stream) {
-    FRL_REQUIRE(n_segs >= 0 && n_tiles >= 0, FRL_E_ARG, "frl_flatten_grads: negative counts");
-    if (n_segs == 0 || n_tiles == 0) return 0;
-    FRL_REQUIRE(segs_dev && tile_prefix_dev && arena_grad, FRL_E_ARG, "frl_flatten_grads: null pointer");
+extern "C" int frl_flatten_grads(const frl_grad_seg* segs_dev, const int64_t* tile_prefix_dev,
+                                 const int32_t* tile_seg_dev, int64_t n_tiles, void* arena_grad, int dst_dtype,
+                                 double scale, void* stream) {
+    FRL_REQUIRE(n_tiles >= 0, FRL_E_ARG, "frl_flatten_grads: negative tile count");
+    if (n_tiles == 0) return 0;
+    FRL_REQUIRE(segs_dev && tile_prefix_dev && tile_seg_dev && arena_grad, FRL_E_ARG, "frl_flatten_grads: null pointer");
     FRL_REQUIRE(dst_dtype == FRL_F32 || dst_dtype == FRL_BF16, FRL_E_DTYPE, "frl_flatten_grads: dst dtype %d", dst_dtype);
     FRL_REQUIRE(aligned16(arena_grad), FRL_E_ALIGN, "frl_flatten_grads: arena must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float sc = static_cast<float>(scale);
     if (dst_dtype == FRL_F32)
         flatten_kernel<f32x4><<<grid_for_tiles(flatten_kernel<f32x4>, n_tiles), kThreads, 0, st>>>(
-            static_cast<f32x4*>(arena_grad), segs_dev, tile_prefix_dev, n_segs, n_tiles, sc);
+            static_cast<f32x4*>(arena_grad), segs_dev, tile_prefix_dev, tile_seg_dev, n_tiles, sc);
     else
         flatten_kernel<bf16x4><<<grid_for_tiles(flatten_kernel<bf16x4>, n_tiles), kThreads, 0, st>>>(
-            static_cast<bf16x4*>(arena_grad), segs_dev, tile_prefix_dev, n_segs, n_tiles, sc);
+            static_cast<bf16x4*>(arena_grad), segs_dev, tile_prefix_dev, tile_seg_dev, n_tiles, sc);
     return after_launch("frl_flatten_grads");
 }
 
 extern "C" int frl_sgd_momentum_mt(float* p, float* buf, void* p_lp, const frl_grad_seg* segs_dev,
-                                   const int64_t* tile_prefix_dev, int n_segs, int64_t n_tiles,
+                                   const int64_t* tile_prefix_dev, const int32_t* tile_seg_dev, int64_t n_tiles,
                                    double lr, double mu, double dampening, double wd, double grad_scale,
                                    const float* grad_scale_dev, const float* dyn, int first_step, void* stream) {
     FRL_REQUIRE(mu == 0.0 || buf != nullptr, FRL_E_ARG, "frl_sgd_momentum_mt: momentum needs buf");
@@ -427,14 +456,14 @@ extern "C" int frl_sgd_momentum_mt(float* p, float* buf, void* p_lp, const frl_g
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float gs = static_cast<float>(grad_scale);
     if (mu != 0.0)
-        return launch_update_mt<SgdRule, 1>(r, p, buf, nullptr, nullptr, p_lp, segs_dev, tile_prefix_dev, n_segs,
+        return launch_update_mt<SgdRule, 1>(r, p, buf, nullptr, nullptr, p_lp, segs_dev, tile_prefix_dev, tile_seg_dev,
                                             n_tiles, gs, grad_scale_dev, dyn, st, "frl_sgd_momentum_mt");
-    return launch_update_mt<SgdRule, 0>(r, p, nullptr, nullptr, nullptr, p_lp, segs_dev, tile_prefix_dev, n_segs,
+    return launch_update_mt<SgdRule, 0>(r, p, nullptr, nullptr, nullptr, p_lp, segs_dev, tile_prefix_dev, tile_seg_dev,
                                         n_tiles, gs, grad_scale_dev, dyn, st, "frl_sgd_momentum_mt");
 }
 
 extern "C" int frl_adam_mt(float* p, float* m, float* v, float* vmax, void* p_lp, const frl_grad_seg* segs_dev,
-                           const int64_t* tile_prefix_dev, int n_segs, int64_t n_tiles, double lr, double beta1,
+                           const int64_t* tile_prefix_dev, const int32_t* tile_seg_dev, int64_t n_tiles, double lr, double beta1,
                            double beta2, double eps, double wd, int64_t step, double grad_scale,
                            const float* grad_scale_dev, const float* dyn, void* stream) {
     FRL_REQUIRE(m && v, FRL_E_ARG, "frl_adam_mt: null state");
@@ -443,15 +472,15 @@ extern "C" int frl_adam_mt(float* p, float* m, float* v, float* vmax, void* p_lp
     const float gs = static_cast<float>(grad_scale);
     if (vmax)
         return launch_update_mt<AdamRule<true>, 3>(make_adam_rule<true>(lr, beta1, beta2, eps, wd, step), p, m, v, vmax,
-                                                   p_lp, segs_dev, tile_prefix_dev, n_segs, n_tiles, gs,
+                                                   p_lp, segs_dev, tile_prefix_dev, tile_seg_dev, n_tiles, gs,
                                                    grad_scale_dev, dyn, st, "frl_adam_mt");
     return launch_update_mt<AdamRule<false>, 2>(make_adam_rule<false>(lr, beta1, beta2, eps, wd, step), p, m, v, nullptr,
-                                                p_lp, segs_dev, tile_prefix_dev, n_segs, n_tiles, gs,
+                                                p_lp, segs_dev, tile_prefix_dev, tile_seg_dev, n_tiles, gs,
                                                 grad_scale_dev, dyn, st, "frl_adam_mt");
 }
 
 extern "C" int frl_rmsprop_mt(float* p, float* sq, float* buf, void* p_lp, const frl_grad_seg* segs_dev,
-                              const int64_t* tile_prefix_dev, int n_segs, int64_t n_tiles, double lr, double alpha,
+                              const int64_t* tile_prefix_dev, const int32_t* tile_seg_dev, int64_t n_tiles, double lr, double alpha,
                               double eps, double wd, double mu, double grad_scale, const float* grad_scale_dev,
                               const float* dyn, void* stream) {
     FRL_REQUIRE(sq, FRL_E_ARG, "frl_rmsprop_mt: null sq");
@@ -460,9 +489,9 @@ extern "C" int frl_rmsprop_mt(float* p, float* sq, float* buf, void* p_lp, const
     const float gs = static_cast<float>(grad_scale);
     if (mu != 0.0)
         return launch_update_mt<RmspropRule<true>, 2>(make_rmsprop_rule<true>(lr, alpha, eps, wd, mu), p, sq, buf, nullptr,
-                                                      p_lp, segs_dev, tile_prefix_dev, n_segs, n_tiles, gs,
+                                                      p_lp, segs_dev, tile_prefix_dev, tile_seg_dev, n_tiles, gs,
                                                       grad_scale_dev, dyn, st, "frl_rmsprop_mt");
     return launch_update_mt<RmspropRule<false>, 1>(make_rmsprop_rule<false>(lr, alpha, eps, wd, mu), p, sq, nullptr, nullptr,
-                                                   p_lp, segs_dev, tile_prefix_dev, n_segs, n_tiles, gs,
+                                                   p_lp, segs_dev, tile_prefix_dev, tile_seg_dev, n_tiles, gs,
                                                    grad_scale_dev, dyn, st, "frl_rmsprop_mt");
 }

@@ -50,6 +50,10 @@ class GradSegTable:
             self._segs[i].numel = s.numel
         self._dev = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         self._prefix_dev = torch.tensor(prefix, dtype=torch.int64, device=device)
+        counts = torch.tensor([b - a for a, b in zip(prefix[:-1], prefix[1:])], dtype=torch.int64)
+        self._tile_seg_dev = torch.repeat_interleave(torch.arange(self.n_segs, dtype=torch.int32),
+                                                     counts).to(device) if self.n_segs else \
+            torch.zeros(1, dtype=torch.int32, device=device)
         self._row_of: Dict[int, int] = {s.index: i for i, s in enumerate(self.slots)}
         self._dirty = True
         self.external = 0            # slots whose gradient currently lies outside the arena
@@ -61,6 +65,10 @@ class GradSegTable:
     @property
     def prefix_dev_ptr(self) -> int:
         return self._prefix_dev.data_ptr()
+
+    @property
+    def tile_seg_dev_ptr(self) -> int:
+        return self._tile_seg_dev.data_ptr()
 
     def point(self, slot, ptr: int, dtype: torch.dtype) -> None:
         row = self._segs[self._row_of[slot.index]]

@@ -93,6 +93,7 @@ class SolverWorkerArgs(NamedTuple):
     cache: Any = None
     precision: Precision = Precision.FP32
     save_every: int = 1
+    graph_step: Optional[bool] = None      # None: FRL_B200_CUDA_GRAPH (default off)
 
 
 def _torch_load(f, **kw):
@@ -201,6 +202,30 @@ def bind_to_gpu_numa_node(local_rank: int) -> bool:
         return False
 
 
+_NORM_FP32_STATS = {}
+
+
+def _norm_accepts_fp32_stats(device: torch.device) -> bool:
+    """Probe once per device: batch_norm with bf16 input and affine parameters but fp32 running
+    statistics (training and eval mode)."""
+    key = str(device)
+    if key not in _NORM_FP32_STATS:
+        try:
+            x = torch.randn(4, 3, 2, 2, device=device).to(torch.bfloat16)
+            w = torch.ones(3, device=device, dtype=torch.bfloat16)
+            b = torch.zeros(3, device=device, dtype=torch.bfloat16)
+            rm, rv = torch.zeros(3, device=device), torch.ones(3, device=device)
+            torch.nn.functional.batch_norm(x, rm, rv, w, b, training=True)
+            torch.nn.functional.batch_norm(x, rm, rv, w, b, training=False)
+            ok = bool(rm.abs().sum() > 0) and rm.dtype == torch.float32
+        except Exception as e:                       # noqa: BLE001
+            logger.info("fp32 BatchNorm statistics next to bf16 parameters are not supported here (%s): "
+                        "running statistics are kept in bf16", str(e).splitlines()[0])
+            ok = False
+        _NORM_FP32_STATS[key] = ok
+    return _NORM_FP32_STATS[key]
+
+
 def resolve_precision(explicit: Optional[Precision] = None) -> Precision:
     if explicit is not None:
         return explicit
@@ -270,7 +295,11 @@ class Solver:
             symm_alloc = try_make_allocator(device, args.world_size)
         arena = ParamArena(model.parameters(), criterion.parameters(), device=device,
                            precision=args.precision, shared_allocator=symm_alloc)
-        if args.precision == Precision.BF16:
+        if args.precision == Precision.BF16 and not _norm_accepts_fp32_stats(device):
+            # BatchNorm running statistics stay fp32 (what the reference's checkpoints hold: a
+            # bf16 EMA with momentum 0.1 stalls on small deltas); only if this torch build
+            # refuses bf16 activations/affine parameters next to fp32 statistics are the buffers
+            # cast — and upcast again on export (arena.exported)
             for buf in model.buffers():
                 if buf.is_floating_point():
                     buf.data = buf.data.to(torch.bfloat16)
@@ -314,8 +343,24 @@ class Solver:
                               node_idx=args.node_idx, node_count=args.node_count,
                               pipeline=pipeline, buffers=buffers, precision=args.precision,
                               serialize_state=(args.local_rank == 0),
-                              graph_step=os.environ.get("FRL_B200_CUDA_GRAPH", "0") == "1")
+                              graph_step=(args.graph_step if args.graph_step is not None
+                                          else os.environ.get("FRL_B200_CUDA_GRAPH", "0") == "1"))
         worker.save_every = args.save_every
+        if args.rank == 0:
+            # one line per run: which of the alternative paths this configuration took
+            logger.info(
+                "frl_b200 step: precision %s | step issue %s | gradient exchange %s | update %s | "
+                "Linear layers with arena-born gradients %d (%d fused with their ReLU) | other "
+                "gradients %s",
+                args.precision.value,
+                "CUDA-graph replay after 3 eager steps" if worker.graphed is not None else "eager launches",
+                ("fused NVLS kernel per bucket (K7), %d buckets" % len(pipeline.buckets)) if pipeline.nvls is not None
+                else ("ncclAllReduce in place + K2 per bucket, %d buckets" % len(pipeline.buckets)) if distributed
+                else "none (1 GPU)",
+                "per bucket on the side stream" if pipeline.eager else "one tail launch",
+                len(pipeline.linear_sites), sum(s.relu is not None for s in pipeline.linear_sites),
+                "read in place through segment tables (K2-mt / one flatten launch per bucket)"
+                if pipeline.mt_enabled else "copied into the arena per tensor")
         scheduler = create_lr_scheduler(run_opts, worker.optimizer,
                                         checkpoint.epoch if checkpoint else -1)
         return worker, scheduler, checkpoint
@@ -517,7 +562,18 @@ class Solver:
     @classmethod
     def solve(cls, run_opts: RunOpts, problem: Problem, *, group_name: Optional[str],
               init_method: str, node_idx: int = 0, node_count: int = 1, memory_quota: int = 0,
-              precision: Optional[Precision] = None) -> Iterator[PerformanceSummary]:
+              precision: Optional[Precision] = None, graph: Optional[bool] = None
+              ) -> Iterator[PerformanceSummary]:
+        """The reference's entry point (solver.py:728-739) plus two keyword-only extensions:
+
+        ``precision``  ``Precision.FP32`` (default; parity with the reference's arithmetic) or
+                       ``Precision.BF16`` (bf16 forward/backward/gradients, fp32 master weights and
+                       optimizer state — the benchmarked configuration).  None: FRL_B200_PRECISION.
+        ``graph``      True: replay the training step from a CUDA graph once a batch signature
+                       has run 3 eager steps (the Problem's forward must be capturable: static
+                       shapes, no host syncs; a failed capture falls back to eager launches).
+                       None: FRL_B200_CUDA_GRAPH (default off).
+        """
         n_visible = 0 if run_opts.cpuonly else _cuda_device_count_without_poisoning_fork()
         if n_visible == 0:
             raise RuntimeError(
@@ -555,7 +611,7 @@ class Solver:
                 node_idx=node_idx, node_count=node_count,
                 rank=node_idx * device_count + local_rank, local_rank=local_rank,
                 world_size=world_size, group_name=group_name, init_method=init_method,
-                cache=None, precision=prec, save_every=save_every)
+                cache=None, precision=prec, save_every=save_every, graph_step=graph)
             if not run_opts.singleThreaded:
                 parent_conn, child_conn = ctx.Pipe(duplex=False)
                 proc = ctx.Process(target=cls._solver_worker_process,

@@ -242,9 +242,27 @@ class SamplerState:
         self._targets: List[List[Tuple[torch.Tensor, ...]]] = []
         self._outputs: List[List[torch.Tensor]] = []
         self._data_metric: DefaultDict[str, list] = defaultdict(list)
+        # Where the fold runs.  The reference calls the Problem's hooks synchronously on the
+        # training thread (solver_worker.py:286-312) and so does this loop by default; a hook that
+        # returns host arrays then costs one pipeline drain per window.  Two ways around it:
+        #   * the hook returns DEVICE tensors (``_fold_device``): nothing is read back until the
+        #     split ends, the fold stays on the training thread/stream and never blocks it;
+        #   * the Problem declares ``metric_hooks_thread_safe = True`` (or FRL_B200_ASYNC_METRICS=1):
+        #     host-returning hooks run on a worker thread + side stream.  Opt-in, because hooks
+        #     that touch the model, global RNGs or backend flags would race with the next steps.
         self._runner: Optional[_MetricWorker] = None
-        if device.type == "cuda" and os.environ.get("FRL_B200_ASYNC_METRICS", "1") != "0":
+        want_async = os.environ.get("FRL_B200_ASYNC_METRICS")
+        if want_async is None:
+            want_async = "1" if getattr(problem, "metric_hooks_thread_safe", False) else "0"
+        if device.type == "cuda" and want_async != "0":
             self._runner = _MetricWorker(device)
+        # device-side state (hooks returning device tensors)
+        self._dev_mode: Optional[bool] = None
+        self._dev_cols: Dict[str, torch.Tensor] = {}
+        self._dev_meta: Dict[str, torch.Tensor] = {}
+        self._host_meta: DefaultDict[str, list] = defaultdict(list)
+        self._dev_random: List[Dict[str, Any]] = []
+        self._dev_worst: Optional[Dict[str, Any]] = None
 
     @staticmethod
     def _cat_metas(metas: List[RawMetas]) -> RawMetas:
@@ -285,7 +303,7 @@ class SamplerState:
             return
         window = (self._metas, self._data, self._outputs, self._targets)
         self._metas, self._data, self._outputs, self._targets = [], [], [], []
-        if self._runner is None:
+        if self._runner is None or self._dev_mode:
             self._fold(*window)
             return
         ready = torch.cuda.Event()
@@ -306,6 +324,8 @@ class SamplerState:
             self._runner.drain()
             self._runner.close()
             self._runner = None
+        if self._dev_mode:
+            self._finish_device()
 
     def _fold(self, metas, data_batches, outputs, targets) -> None:
         meta = self._problem.refine_batch_meta(self._cat_metas(metas))
@@ -320,6 +340,13 @@ class SamplerState:
 
         sample_metric = self._problem.compute_batch_metrics(
             meta=meta, target=target, output=output, device=self._device)
+        if self._dev_mode is None:
+            self._dev_mode = bool(sample_metric) and all(
+                torch.is_tensor(v) and v.is_cuda for v in sample_metric.values())
+        if self._dev_mode:
+            self._fold_device(meta, data_batches, starts, n_group, target, output, sample_metric)
+            self._cur_samples += n_group
+            return
         if sample_metric is not None:
             for k, v in sample_metric.items():
                 self._data_metric[k].append(np.asarray(v))     # joined once, at the epoch's end
@@ -347,6 +374,136 @@ class SamplerState:
                     heapq.heappushpop(self._worst_samples, (score, self._one(
                         int(i), data_batches, starts, target, output, meta, sample_metric)))
         self._cur_samples += n_group
+
+    # -- device-side fold ----------------------------------------------------------
+    # The Problem's hook returned per-sample metrics as DEVICE tensors: they go into
+    # [n_samples] device columns, the random picks are row-gathered by host-known positions, the
+    # worst-k set is kept as running device buffers merged per window with ``topk`` — no
+    # device-to-host read, no host sync until ``finish()`` reads everything back once.
+    @staticmethod
+    def _gather_rows(batches: List[torch.Tensor], starts: List[int], idx: torch.Tensor) -> torch.Tensor:
+        """Rows ``idx`` (device int64, window-relative) of the un-concatenated minibatch list."""
+        out = None
+        for b, start in zip(batches, starts):
+            rows = b.index_select(0, (idx - start).clamp_(0, len(b) - 1))
+            if out is None:
+                out = rows
+            else:
+                inside = ((idx >= start) & (idx < start + len(b))).view(-1, *([1] * (rows.dim() - 1)))
+                out = torch.where(inside, rows, out)
+        return out
+
+    def _pick(self, idx: torch.Tensor, data_batches, starts, target, output, meta, sample_metric):
+        n_fields = len(data_batches[0])
+        return {"pos": idx + self._cur_samples,
+                "data": [self._gather_rows([d[f] for d in data_batches], starts, idx) for f in range(n_fields)],
+                "target": [tuple(t.index_select(0, idx) for t in head) for head in target],
+                "output": [o.index_select(0, idx) for o in output],
+                "metric": {k: v.reshape(len(v), -1)[:, 0].index_select(0, idx) if v.dim() > 1
+                           else v.index_select(0, idx) for k, v in sample_metric.items()},
+                "meta": {k: v.index_select(0, idx) for k, v in meta._asdict().items()
+                         if torch.is_tensor(v) and v.is_cuda}}
+
+    @staticmethod
+    def _cat_picks(a, b):
+        return {"pos": torch.cat([a["pos"], b["pos"]]),
+                "data": [torch.cat([x, y]) for x, y in zip(a["data"], b["data"])],
+                "target": [tuple(torch.cat([x, y]) for x, y in zip(ha, hb))
+                           for ha, hb in zip(a["target"], b["target"])],
+                "output": [torch.cat([x, y]) for x, y in zip(a["output"], b["output"])],
+                "metric": {k: torch.cat([a["metric"][k], b["metric"][k]]) for k in a["metric"]},
+                "meta": {k: torch.cat([a["meta"][k], b["meta"][k]]) for k in a["meta"]}}
+
+    @staticmethod
+    def _take(p, sel):
+        return {"pos": p["pos"].index_select(0, sel),
+                "data": [x.index_select(0, sel) for x in p["data"]],
+                "target": [tuple(x.index_select(0, sel) for x in head) for head in p["target"]],
+                "output": [x.index_select(0, sel) for x in p["output"]],
+                "metric": {k: v.index_select(0, sel) for k, v in p["metric"].items()},
+                "meta": {k: v.index_select(0, sel) for k, v in p["meta"].items()}}
+
+    def _fold_device(self, meta, data_batches, starts, n_group, target, output, sample_metric) -> None:
+        base, dev = self._cur_samples, self._device
+        for k, v in sample_metric.items():
+            col = self._dev_cols.get(k)
+            if col is None:
+                col = self._dev_cols[k] = torch.zeros(self._n_samples, dtype=torch.float32, device=dev)
+            col[base:base + n_group] = v.reshape(n_group).float()
+        for k, v in meta._asdict().items():
+            if v is None:
+                continue
+            if torch.is_tensor(v) and v.is_cuda:
+                col = self._dev_meta.get(k)
+                if col is None:
+                    col = self._dev_meta[k] = torch.zeros((self._n_samples,) + tuple(v.shape[1:]),
+                                                          dtype=v.dtype, device=dev)
+                col[base:base + n_group] = v
+            else:            # host-side meta (names, ids as lists / CPU tensors): kept for the split
+                self._host_meta[k].extend(v.tolist() if torch.is_tensor(v) else list(v))
+        if self._n_vis <= 0:
+            return
+        picks = sorted(j - base for j in self._random_indices if base <= j < base + n_group)
+        if picks:
+            idx = torch.tensor(picks, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+            self._dev_random.append(self._pick(idx, data_batches, starts, target, output, meta, sample_metric))
+        # worst-k of this window, merged into the running set: all on the device
+        scores = sample_metric[self._rankable_metric].reshape(n_group).float()
+        if self._ordering == Ordering.DESC:
+            valid = torch.ones_like(scores, dtype=torch.bool) if self._allow_non_positive_definite else scores >= 0
+            scores = -scores
+        else:
+            valid = torch.ones_like(scores, dtype=torch.bool) if self._allow_non_positive_definite else scores >= 0
+        scores = torch.where(valid, scores, torch.full_like(scores, float("-inf")))
+        k = min(self._n_vis, n_group)
+        top_scores, top_idx = torch.topk(scores, k)
+        cand = self._pick(top_idx, data_batches, starts, target, output, meta, sample_metric)
+        cand["score"] = top_scores
+        if self._dev_worst is None:
+            self._dev_worst = cand
+        else:
+            merged = self._cat_picks(self._dev_worst, cand)
+            merged_scores = torch.cat([self._dev_worst["score"], top_scores])
+            keep_scores, sel = torch.topk(merged_scores, min(self._n_vis, merged_scores.numel()))
+            self._dev_worst = self._take(merged, sel)
+            self._dev_worst["score"] = keep_scores
+
+    def _finish_device(self) -> None:
+        """The split's single device-to-host read: metric columns, the picks, the worst-k set."""
+        torch.cuda.current_stream(self._device).synchronize()
+        cols = {k: v[:self._cur_samples].cpu().numpy() for k, v in self._dev_cols.items()}
+        for k, v in cols.items():
+            self._data_metric[k] = [v]
+        dev_meta = {k: v[:self._cur_samples].cpu() for k, v in self._dev_meta.items()}
+
+        def samples_of(p, limit=None) -> List[SingleSample]:
+            pos = p["pos"].cpu().tolist()
+            data = [x.cpu() for x in p["data"]]
+            target = [tuple(x.cpu() for x in head) for head in p["target"]]
+            output = [x.float().cpu() for x in p["output"]]
+            out = []
+            for r, g in enumerate(pos):
+                if limit is not None and not limit[r]:
+                    continue
+                meta = {k: v[g] for k, v in dev_meta.items()}
+                meta.update({k: v[g] for k, v in self._host_meta.items()})
+                out.append(SingleSample(data=[x[r] for x in data], target=[tuple(x[r] for x in h) for h in target],
+                                        meta=meta, output=[x[r] for x in output],
+                                        metric={k: cols[k][g] for k in cols}))
+            return out
+
+        for p in self._dev_random:
+            self._random_samples.extend(samples_of(p))
+        if self._dev_worst is not None:
+            finite = torch.isfinite(self._dev_worst["score"]).cpu().tolist()      # -inf = filtered out
+            scores = self._dev_worst["score"].cpu().tolist()
+            kept = samples_of(self._dev_worst, finite)
+            kept_scores = [s for s, f in zip(scores, finite) if f]
+            # heap order of the host path is unspecified beyond "the k most extreme": sort
+            # ascending by score like a drained min-heap would come out
+            order = sorted(range(len(kept)), key=lambda i: kept_scores[i])
+            self._worst_samples = [(kept_scores[i], kept[i]) for i in order]
+        self._dev_random, self._dev_worst = [], None
 
     @property
     def n_samples(self) -> int:
@@ -701,7 +858,7 @@ class SolverWorker:
             self.model.eval()
             self.pipeline.unpatch_linears()          # pickle plain nn.Linear modules
             try:
-                with self.arena.exported(cpu=True):
+                with self.arena.exported(cpu=True, module=self.model):
                     with io.BytesIO() as buf:
                         torch.save(self.model, buf)
                         model_bytes = buf.getvalue()
@@ -768,7 +925,18 @@ class SolverWorker:
                 out_dtype = torch.bfloat16 if self.precision == Precision.BF16 else torch.float32
                 loaders[split] = DeviceBatchLoader(dataset, batch_size=batchSize, sampler=sampler,
                                                    device=self.device, out_dtype=out_dtype)
+                ld = loaders[split]
+                logger.info("input path for split %s: batched device loader (%s%s), wire dtypes %s",
+                            split.value, ld.path,
+                            ", %d gather threads" % ld.threads if ld.path == "host" else ", %d CTAs" % ld.blocks,
+                            {k: str(v).replace("torch.", "") for k, v in ld._wire_dtype.items()})
                 continue
+            if self.device.type == "cuda":
+                logger.warning(
+                    "input path for split %s: per-sample DataLoader (__getitem__ + Python transform + "
+                    "collate, as the reference) — the dataset does not expose `pinned_fields` + a "
+                    "`device_transform` (transform.DeviceBatchTransform), so the host, not the B200, "
+                    "sets the step rate at large batches", split.value)
             loaders[split] = torch.utils.data.DataLoader(
                 dataset, batch_size=batchSize, shuffle=sampler is None,
                 num_workers=self.run_opts.numThreads,

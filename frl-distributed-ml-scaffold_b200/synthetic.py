@@ -194,8 +194,11 @@ def _task_classes(ns):
             return (tensors[self._field],), IndexMeta(index=tensors["index"])
 
         def compute_batch_metrics(self, meta, target, output):
-            err = (output.float() - target[0].float()) ** 2
-            return {self.name + "_MSE": err.reshape(len(err), -1).mean(1).cpu().numpy()}
+            err = ((output.float() - target[0].float()) ** 2).reshape(len(output), -1).mean(1)
+            # device outputs -> device metrics: the loop keeps them in HBM and reads the whole
+            # split back once (SamplerState's device-side fold); host outputs -> the reference's
+            # numpy arrays
+            return {self.name + "_MSE": err if err.is_cuda else err.numpy()}
 
         @property
         def rankable_metrics(self):
@@ -229,7 +232,7 @@ def _task_classes(ns):
 
         def compute_batch_metrics(self, meta, target, output):
             wrong = (output.argmax(1) != target[0]).float()
-            return {self.name + "_err": wrong.cpu().numpy()}
+            return {self.name + "_err": wrong if wrong.is_cuda else wrong.numpy()}
 
         @property
         def rankable_metrics(self):

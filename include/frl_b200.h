@@ -88,8 +88,9 @@ int frl_rmsprop(float* p, const void* g, float* sq, float* buf, void* p_lp, int6
  * torch Reducer) for parameters whose gradients autograd allocates itself (convolutions,
  * normalisation layers): a SEGMENT TABLE in device memory names, per parameter tensor, where its
  * gradient lies, its dtype, its arena offset (a multiple of 8 elements) and its length.
- *   tile_prefix_dev[s] = number of tiles of segments 0..s-1, n_segs + 1 entries, a tile being
- *   frl_mt_tile_elems() arena elements of ONE segment; n_tiles = tile_prefix_dev[n_segs].
+ *   tile_prefix_dev[s] = number of tiles of segments 0..s-1 (int64, n_segs + 1 entries), a tile
+ *   being frl_mt_tile_elems() arena elements of ONE segment; n_tiles = tile_prefix_dev[n_segs];
+ *   tile_seg_dev[t] = segment index of tile t (int32, n_tiles entries).
  *   Gradient pointers must be 16-byte aligned; tensors contiguous in the parameter's layout.
  * frl_flatten_grads : arena_grad[arena_off + i] = cast(g[i] * scale) for every segment, one launch.
  * frl_*_mt          : the K2 update of the listed segments reading g in place; p / state / p_lp
@@ -105,21 +106,22 @@ typedef struct frl_grad_seg {
 
 int64_t frl_mt_tile_elems(void);
 
-int frl_flatten_grads(const frl_grad_seg* segs_dev, const int64_t* tile_prefix_dev, int n_segs,
-                      int64_t n_tiles, void* arena_grad, int dst_dtype, double scale, void* stream);
+int frl_flatten_grads(const frl_grad_seg* segs_dev, const int64_t* tile_prefix_dev,
+                      const int32_t* tile_seg_dev, int64_t n_tiles, void* arena_grad, int dst_dtype,
+                      double scale, void* stream);
 
 int frl_sgd_momentum_mt(float* p, float* buf, void* p_lp, const frl_grad_seg* segs_dev,
-                        const int64_t* tile_prefix_dev, int n_segs, int64_t n_tiles,
+                        const int64_t* tile_prefix_dev, const int32_t* tile_seg_dev, int64_t n_tiles,
                         double lr, double mu, double dampening, double wd, double grad_scale,
                         const float* grad_scale_dev, const float* dyn, int first_step, void* stream);
 
 int frl_adam_mt(float* p, float* m, float* v, float* vmax, void* p_lp, const frl_grad_seg* segs_dev,
-                const int64_t* tile_prefix_dev, int n_segs, int64_t n_tiles, double lr, double beta1,
+                const int64_t* tile_prefix_dev, const int32_t* tile_seg_dev, int64_t n_tiles, double lr, double beta1,
                 double beta2, double eps, double wd, int64_t step, double grad_scale,
                 const float* grad_scale_dev, const float* dyn, void* stream);
 
 int frl_rmsprop_mt(float* p, float* sq, float* buf, void* p_lp, const frl_grad_seg* segs_dev,
-                   const int64_t* tile_prefix_dev, int n_segs, int64_t n_tiles, double lr, double alpha,
+                   const int64_t* tile_prefix_dev, const int32_t* tile_seg_dev, int64_t n_tiles, double lr, double alpha,
                    double eps, double wd, double mu, double grad_scale, const float* grad_scale_dev,
                    const float* dyn, void* stream);
 

@@ -174,3 +174,34 @@ def test_model_helpers():
     assert torch.equal(model.MulConstant(2.0)(torch.ones(2)), torch.full((2,), 2.0))
     with pytest.raises(AssertionError):
         model.ListSelect(sel_index=0, num_elements=2)([torch.zeros(1)])
+
+
+# ---- SamplerState against the fixtures recorded from the live reference class ---------------------
+
+
+
+
+@pytest.mark.parametrize("config", ["err_MSE_DESC", "score_ASC", "score_DESC"])
+def test_sampler_state_host_path_matches_reference_fixture(golden_dir, config):
+    """tests/golden/sampler_state.json = what the unmodified reference's SamplerState produced for
+    the shared scenario (oracle/make_sampler_state_golden.py): per-sample metrics, random picks
+    and worst-k set of this repo's class must be the same (host arrays from the hook)."""
+    import json
+    import random
+    import numpy as np
+    import torch
+    import frl_b200.solver_worker as sw
+    from frl_b200.problem import Ordering
+    from oracle import make_sampler_state_golden as gen
+    want = json.load(open(os.path.join(golden_dir, "sampler_state.json")))[config]
+    name, ordering = config.rsplit("_", 1)
+    batches, total = gen.scenario()
+    random.seed(gen.PY_SEED)
+    mine = sw.SamplerState(gen.make_problem(Ordering, name, ordering), total, total, torch.device("cpu"),
+                           gen.N_VIS)
+    gen.drive(mine, batches)
+    mine.finish()
+    for k, v in want["metrics"].items():
+        np.testing.assert_array_equal(np.asarray(mine.data_metric[k], dtype=np.float64), np.asarray(v))
+    assert [int(s.meta["index"]) for s in mine.random_samples] == want["random_ids"]
+    assert sorted(int(s.meta["index"]) for s in mine.worst_samples) == want["worst_ids"]

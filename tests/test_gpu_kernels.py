@@ -415,6 +415,8 @@ def test_linear_gradients_are_written_into_the_arena(precision, monkeypatch):
         pipe = grad_sync.GradBucketPipeline(arena, opt, bucket_cap_mb=0.004, eager_update=direct)
         if direct:
             assert pipe.patch_linears(net) == 3 and len(pipe.buckets) > 1
+        else:
+            pipe.mt_enabled = False       # reference point: autograd's gradients copied into the arena
         x = x0.to(torch.bfloat16) if prec == Precision.BF16 else x0
         for _ in range(3):
             pipe.begin_step()

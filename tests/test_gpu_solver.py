@@ -328,3 +328,43 @@ def test_fused_linear_relu_units_keep_reference_parity(ns, golden_dir, monkeypat
         out = whole([x])                                   # pickled module: stock forward, ReLUs active
     assert all("forward" not in m.__dict__ for m in whole.modules())
     assert len(out) == 2 and out[0].shape == (5, 4)
+
+
+@pytest.mark.parametrize("config", ["err_MSE_DESC", "score_ASC", "score_DESC"])
+def test_device_side_sampler_state_matches_reference_fixture(golden_dir, config):
+    """the Problem's hook returns DEVICE tensors; per-sample metrics stay in HBM
+    columns, the worst-k set is a running device buffer merged with topk per window, everything is
+    read back once at the end of the split.  Same fixtures as the host path: the reference's own
+    SamplerState on the same scenario (oracle/make_sampler_state_golden.py)."""
+    import json
+    import random
+    import frl_b200.solver_worker as sw
+    from frl_b200.problem import Ordering
+    from oracle import make_sampler_state_golden as gen
+    want = json.load(open(os.path.join(golden_dir, "sampler_state.json")))[config]
+    name, ordering = config.rsplit("_", 1)
+    batches, total = gen.scenario()
+    dev = torch.device("cuda", 0)
+    cuda_batches = [dict(meta={k: v.to(dev) for k, v in b["meta"].items()},
+                         data=[t.to(dev) for t in b["data"]],
+                         outputs=[t.to(dev) for t in b["outputs"]],
+                         targets=[tuple(t.to(dev) for t in h) for h in b["targets"]]) for b in batches]
+    random.seed(gen.PY_SEED)
+    mine = sw.SamplerState(gen.make_problem(Ordering, name, ordering, as_numpy=False), total, total, dev,
+                           gen.N_VIS)
+    gen.drive(mine, cuda_batches)
+    assert mine._dev_mode is True and mine._runner is None        # no worker thread, no host read so far
+    assert not mine.random_samples and not mine.worst_samples
+    mine.finish()
+    for k, v in want["metrics"].items():
+        np.testing.assert_allclose(np.asarray(mine.data_metric[k], dtype=np.float64), np.asarray(v),
+                                   rtol=1e-6, atol=1e-7)
+    assert [int(s.meta["index"]) for s in mine.random_samples] == want["random_ids"]
+    assert sorted(int(s.meta["index"]) for s in mine.worst_samples) == want["worst_ids"]
+    # the captured samples are the scenario's rows, bit for bit
+    rows = {int(i): (b["data"][0][j], b["outputs"][0][j], b["targets"][1][0][j])
+            for b in batches for j, i in enumerate(b["meta"]["index"])}
+    for s in mine.random_samples + mine.worst_samples:
+        d, o, t = rows[int(s.meta["index"])]
+        assert torch.equal(s.data[0], d) and torch.equal(s.output[0], o) and torch.equal(s.target[1][0], t)
+        assert not s.data[0].is_cuda

@@ -81,6 +81,54 @@ def bench_k2(iters):
     return out
 
 
+def bench_k2mt(iters):
+    """K2-mt / K1 on the parameter lists of BASELINE configs 4/5: 62 / 167 tensors, gradients in
+    separately allocated bf16 tensors (what cuDNN hands to autograd), segment table in HBM."""
+    import torchvision
+    from frl_b200.multi_tensor import GradSegTable
+
+    class Slot:
+        def __init__(self, index, offset, numel):
+            self.index, self.offset, self.numel = index, offset, numel
+
+    out = []
+    for label, arch, heads, algo in (("r18", "resnet18", [(512, 1000)], "sgd"),
+                                     ("r50x4", "resnet50", [(2048, 1000), (2048, 100), (2048, 10), (2048, 4)], "adam")):
+        net = getattr(torchvision.models, arch)(weights=None)
+        sizes = [p.numel() for n, p in net.named_parameters() if not n.startswith("fc.")]
+        for i, o in heads:
+            sizes += [i * o, o]
+        slots, off = [], 0
+        for i, n in enumerate(sizes):
+            slots.append(Slot(i, off, n))
+            off = (off + n + 7) // 8 * 8
+        n = off
+        grads = [torch.randn(s.numel, device=DEV).bfloat16() for s in slots]
+        table = GradSegTable(slots, DEV)
+        for s_, g in zip(slots, grads):
+            table.point(s_, g.data_ptr(), g.dtype)
+        table.upload()
+        p = torch.randn(n, device=DEV)
+        lp = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+        s0, s1 = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+        flat = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+        n_real = sum(sizes)
+        if algo == "sgd":
+            def fn(i, p=p, s0=s0, lp=lp, table=table):
+                _native.sgd_momentum_mt(p, s0, lp, table, lr=0.01, mu=0.9, dampening=0.0, wd=1e-5, first_step=False)
+            bpp = 20
+        else:
+            def fn(i, p=p, s0=s0, s1=s1, lp=lp, table=table):
+                _native.adam_mt(p, s0, s1, None, lp, table, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, wd=1e-5, step=3)
+            bpp = 28
+        out.append(timed("K2-mt %s %s: %d tensors, %d params, gradients read in place" % (algo, label, len(sizes), n_real),
+                         fn, 1, bpp * n_real, iters))
+        out.append(timed("K1 flatten_grads %s: %d tensors -> bf16 arena, one launch" % (label, len(sizes)),
+                         lambda i, table=table, flat=flat: _native.flatten_grads(table, flat, scale=1.0), 1,
+                         4 * n_real, iters))
+    return out
+
+
 def bench_k3(iters):
     n = 54_703_144
     out = []
@@ -192,13 +240,13 @@ def bench_k8(iters):
     return out
 
 
-BENCHES = {"k2": bench_k2, "k3": bench_k3, "k4": bench_k4, "k5": bench_k5, "k6": bench_k6,
+BENCHES = {"k2": bench_k2, "k2mt": bench_k2mt, "k3": bench_k3, "k4": bench_k4, "k5": bench_k5, "k6": bench_k6,
            "k8": bench_k8}
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="k2,k3,k4,k5,k6,k8")
+    ap.add_argument("--only", default="k2,k2mt,k3,k4,k5,k6,k8")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--json", default=None)
     ap.add_argument("--warmup", type=int, default=3)
