@@ -279,6 +279,9 @@ class DeviceBatchLoader:
     def __iter__(self) -> Iterator[Tuple[List[torch.Tensor], List[Tuple[torch.Tensor, ...]], dict]]:
         split: Split = self.dataset.data_type
         transform: DeviceBatchTransform = self.dataset.device_transform
+        import time as _time
+        t_iter = _time.perf_counter()
+        trace = os.environ.get("FRL_B200_EPOCH_TRACE")
         for ev in self._freed:
             ev.record()
         batches = self._index_batches()
@@ -320,9 +323,14 @@ class DeviceBatchLoader:
                 k_up += 1
 
             advance()
+        if trace:
+            print("loader trace: first upload issued %.2f ms after iter()" % (1e3 * (_time.perf_counter() - t_iter)),
+                  flush=True)
         k = 0
         while uploaded:
             advance()                             # keep the next transfers in flight
+            if trace and k == 0:
+                print("loader trace: second upload issued %.2f ms" % (1e3 * (_time.perf_counter() - t_iter)), flush=True)
             n = uploaded.popleft()
             s = k % self.depth
             slot = self._slots[s]
@@ -338,6 +346,8 @@ class DeviceBatchLoader:
             data = [keep(t) for t in data]
             target = [tuple(keep(t) for t in head) for head in target]
             meta = {k: keep(v) for k, v in meta.items()}
+            if trace and k == 0:
+                print("loader trace: first batch ready to yield %.2f ms" % (1e3 * (_time.perf_counter() - t_iter)), flush=True)
             yield data, target, meta
             # the consumer has issued everything that reads this slot: let the copy stream reuse it
             self._freed[s].record()
