@@ -180,7 +180,10 @@ class ParamArena:
                 ) -> List[Tuple[int, int]]:
         """Contiguous element ranges ``[lo, hi)`` covering the arena, listed in the order their
         gradients become ready (last parameters first), each at most ``cap_bytes`` of gradient
-        (a single larger tensor gets its own bucket)."""
+        (a single larger tensor gets its own bucket).  A bucket that is still tiny (< 1 % of the
+        cap: a lone bias) when the next tensor would overflow it absorbs that tensor instead of
+        closing: a layer's bias and weight gradients are produced by the same backward call, and
+        every bucket costs a launch and, with the fused NVLS step, two cross-GPU barriers."""
         esz = 2 if self.grad_dtype == torch.bfloat16 else 4
         out: List[Tuple[int, int]] = []
         hi = self.numel
@@ -188,6 +191,11 @@ class ParamArena:
         cap = first_cap_bytes or cap_bytes
         for s in reversed(self.slots):
             if (hi - s.offset) * esz > cap and cur_lo < hi:
+                if (hi - cur_lo) * esz * 100 < cap_bytes:      # tiny open bucket: take the tensor in
+                    out.append((s.offset, hi))
+                    hi = cur_lo = s.offset
+                    cap = cap_bytes
+                    continue
                 out.append((cur_lo, hi))
                 hi = cur_lo
                 cap = cap_bytes

@@ -22,6 +22,8 @@
 // in every peer's pad and consumes flag `peer` in its own (CAS 0->1 / 1->0, system scope), then
 // releases / collects the other blocks through local flags, so the grid can span every SM.
 // Data movement is 16 bytes per multimem instruction.
+#include <stdlib.h>
+
 #include "frl_common.cuh"
 #include "optim_rules.cuh"
 
@@ -50,8 +52,8 @@ __device__ __forceinline__ void meet_peers_block0(uint32_t* const* pads, int ran
         uint32_t* put = pads[peer] + base + rank;
         uint32_t* wait = pads[rank] + base + peer;
         __threadfence_system();                                   // release everything before
-        while (atomicCAS_system(put, 0u, 1u) != 0u) {}
-        while (atomicCAS_system(wait, 1u, 0u) != 1u) {}
+        while (atomicCAS_system(put, 0u, 1u) != 0u) { __nanosleep(100); }
+        while (atomicCAS_system(wait, 1u, 0u) != 1u) { __nanosleep(100); }
         __threadfence_system();                                   // acquire everything after
     }
     __syncthreads();
@@ -66,7 +68,7 @@ __device__ __forceinline__ void kernel_entry_barrier(uint32_t* const* pads, int 
             atomicExch(local + 8 + b, 1u);                        // release the other blocks
     } else {
         if (threadIdx.x == 0) {
-            while (atomicCAS(local + 8 + blockIdx.x, 1u, 0u) != 1u) {}
+            while (atomicCAS(local + 8 + blockIdx.x, 1u, 0u) != 1u) { __nanosleep(200); }
             __threadfence();
         }
     }
@@ -84,7 +86,7 @@ __device__ __forceinline__ void kernel_exit_barrier(uint32_t* const* pads, int r
         return;
     }
     if (threadIdx.x == 0) {
-        while (atomicAdd(local, 0u) != gridDim.x - 1) {}
+        while (atomicAdd(local, 0u) != gridDim.x - 1) { __nanosleep(100); }
         atomicExch(local, 0u);
         __threadfence_system();
     }
@@ -106,9 +108,11 @@ struct NvlsCommon {
 // The switch round trip of multimem.ld_reduce is the long latency here (microseconds), so every
 // thread first issues kNRemote of them back to back and only then walks the items, loading the
 // (short-latency) local master/state slices item by item.
-constexpr int kNRemote = 4;
-
-template <typename Rule, int NS>
+// How many: NVLink wants ~2.3 MB in flight per GPU (770 GB/s x ~3 us).  The grid is kept small on
+// purpose (CTAs parked at the entry barrier cost the overlapped backward GEMMs their SMs), so the
+// depth per thread makes up for it: 16 CTAs x 512 threads x kNRemote x 16 B = 0.5 MB at 4, 2 MB at
+// 16.  At world 2 a rank's shard is half of every bucket (4x the work per rank of world 8).
+template <typename Rule, int NS, int kNRemote>
 __global__ void __launch_bounds__(kNThreads)
 nvls_update_bf16(float* __restrict__ p_, float* __restrict__ s0_, float* __restrict__ s1_,
                  float* __restrict__ s2_, const __nv_bfloat16* mc_g, __nv_bfloat16* mc_lp,
@@ -168,7 +172,7 @@ nvls_update_bf16(float* __restrict__ p_, float* __restrict__ s0_, float* __restr
 }
 
 // FP32 mode: fp32 gradients in, parameters ARE the master: multicast the new fp32 weights.
-template <typename Rule, int NS>
+template <typename Rule, int NS, int kNRemote>
 __global__ void __launch_bounds__(kNThreads)
 nvls_update_f32(const float* __restrict__ p_, float* __restrict__ s0_, float* __restrict__ s1_,
                 float* __restrict__ s2_, const float* mc_g, float* mc_p, Rule rule, NvlsCommon c) {
@@ -231,13 +235,26 @@ static int launch_nvls(const Rule& rule, float* p, float* s0, float* s1, float* 
                  world, pad_base, (flags & FRL_NVLS_EXTERNAL_SYNC) ? 0 : 1, n,
                  static_cast<float>(gscale), dyn};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // remote loads in flight per thread: FRL_B200_NVLS_INFLIGHT (4 | 8 | 16), default by world size
+    static const int env_depth = [] {
+        const char* e = getenv("FRL_B200_NVLS_INFLIGHT");
+        return e ? atoi(e) : 0;
+    }();
+    const int depth = env_depth > 0 ? env_depth : (world <= 2 ? 16 : (world <= 4 ? 8 : 4));
     // the grid must be identical on every rank: it depends on arguments only
-    if (g_dtype == FRL_BF16)
-        nvls_update_bf16<Rule, NS><<<max_blocks, kNThreads, 0, st>>>(
-            p, s0, s1, s2, static_cast<const __nv_bfloat16*>(mc_g), static_cast<__nv_bfloat16*>(mc_out), rule, c);
-    else
-        nvls_update_f32<Rule, NS><<<max_blocks, kNThreads, 0, st>>>(
-            p, s0, s1, s2, static_cast<const float*>(mc_g), static_cast<float*>(mc_out), rule, c);
+#define FRL_NV(NR)                                                                                    \
+    do {                                                                                              \
+        if (g_dtype == FRL_BF16)                                                                      \
+            nvls_update_bf16<Rule, NS, NR><<<max_blocks, kNThreads, 0, st>>>(                         \
+                p, s0, s1, s2, static_cast<const __nv_bfloat16*>(mc_g), static_cast<__nv_bfloat16*>(mc_out), rule, c); \
+        else                                                                                          \
+            nvls_update_f32<Rule, NS, NR><<<max_blocks, kNThreads, 0, st>>>(                          \
+                p, s0, s1, s2, static_cast<const float*>(mc_g), static_cast<float*>(mc_out), rule, c); \
+    } while (0)
+    if (depth >= 16) FRL_NV(16);
+    else if (depth >= 8) FRL_NV(8);
+    else FRL_NV(4);
+#undef FRL_NV
     return after_launch(name);
 }
 
