@@ -57,7 +57,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=None, help="gradient bucket cap (MiB)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph (1) or issue it eagerly (0)")
-    ap.add_argument("--profile", default=None, help="write a torch.profiler chrome trace of 5 steps here")
+    ap.add_argument("--profile", default=None,
+                    help="write a JSON summary (device time per kernel per step, torch.profiler over 5 steps) here")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.algo is None:
@@ -730,7 +731,9 @@ def main_b200(args, rank, local_rank, world):
                             "backward; the single-GPU run carries the HBM roofline of the update kernel (K2)")
 
     if args.profile:
-        # every rank runs the steps (collectives!); only rank 0 records
+        # every rank runs the steps (collectives!); only rank 0 records.  Output: a JSON summary of
+        # device time per kernel per step (same format as the torch-gpu arm writes) for the
+        # kernel-by-kernel attribution of the step-time difference.
         from contextlib import nullcontext
         from torch.profiler import ProfilerActivity, profile
         ctx = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) if rank == 0 else nullcontext()
@@ -739,7 +742,12 @@ def main_b200(args, rank, local_rank, world):
                 step_resident(W + K + i)
             torch.cuda.synchronize()
         if rank == 0:
-            prof.export_chrome_trace(args.profile)
+            rows = sorted(((e.key, e.device_time_total / 5.0, e.count / 5.0) for e in prof.key_averages()
+                           if e.device_time_total > 0), key=lambda r: -r[1])
+            with open(args.profile, "w") as f:
+                json.dump({"impl": "b200", "ms_per_step": total_ms / K, "kernels_us_per_step":
+                           [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:40]]},
+                          f, indent=1)
             log(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25))
     barrier()
 
@@ -801,14 +809,18 @@ def main_b200(args, rank, local_rank, world):
         e2e_ms = max_over_ranks(m0.elapsed_time(m1))
         ep_losses = stats[t.Split.TRAIN].losses
         assert all(v == v for v in ep_losses.values()), "NaN loss in the e2e leg"
-        if args.profile and rank == 0:
+        if args.profile and world == 1:
             from torch.profiler import ProfilerActivity, profile
             with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
                 worker.cur_epoch += 1
                 worker._pass_one_epoch(host_problem, loaders, Mode.TRAIN)
                 torch.cuda.synchronize()
-            prof.export_chrome_trace(args.profile.replace(".json", "") + "_e2e.json")
-            log(prof.key_averages().table(sort_by="cuda_time_total", row_limit=20))
+            rows = sorted(((e.key, e.device_time_total / L, e.count / L) for e in prof.key_averages()
+                           if e.device_time_total > 0), key=lambda r: -r[1])
+            with open(args.profile.replace(".json", "") + "_e2e.json", "w") as f:
+                json.dump({"impl": "b200 e2e epoch", "steps": L, "kernels_us_per_step":
+                           [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:40]]},
+                          f, indent=1)
         n_metrics = len(stats[t.Split.TRAIN].metrics)
         e2e = {"value": world * B * e2e_steps / (e2e_ms / 1e3), "unit": "samples/s",
                "h2d_bytes_per_step": h2d_bytes,

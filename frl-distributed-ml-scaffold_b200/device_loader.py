@@ -325,12 +325,12 @@ class DeviceBatchLoader:
             advance()
         if trace:
             print("loader trace: first upload issued %.2f ms after iter()" % (1e3 * (_time.perf_counter() - t_iter)),
-                  flush=True)
+                  flush=True, file=__import__("sys").stderr)
         k = 0
         while uploaded:
             advance()                             # keep the next transfers in flight
             if trace and k == 0:
-                print("loader trace: second upload issued %.2f ms" % (1e3 * (_time.perf_counter() - t_iter)), flush=True)
+                print("loader trace: second upload issued %.2f ms" % (1e3 * (_time.perf_counter() - t_iter)), flush=True, file=__import__("sys").stderr)
             n = uploaded.popleft()
             s = k % self.depth
             slot = self._slots[s]
@@ -347,7 +347,7 @@ class DeviceBatchLoader:
             target = [tuple(keep(t) for t in head) for head in target]
             meta = {k: keep(v) for k, v in meta.items()}
             if trace and k == 0:
-                print("loader trace: first batch ready to yield %.2f ms" % (1e3 * (_time.perf_counter() - t_iter)), flush=True)
+                print("loader trace: first batch ready to yield %.2f ms" % (1e3 * (_time.perf_counter() - t_iter)), flush=True, file=__import__("sys").stderr)
             yield data, target, meta
             # the consumer has issued everything that reads this slot: let the copy stream reuse it
             self._freed[s].record()

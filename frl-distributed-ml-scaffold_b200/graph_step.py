@@ -66,7 +66,8 @@ class GraphedTrainStep:
             # not capturable (host sync in the Problem's forward, a stale autograd graph bound
             # to another stream, ...): stay on the eager path for the rest of the run
             logger.warning("CUDA-graph capture of the training step failed (%s); "
-                           "continuing with eager launches", str(e).splitlines()[0])
+                           "continuing with eager launches", str(e).splitlines()[0],
+                           exc_info=bool(__import__("os").environ.get("FRL_B200_DEBUG")))
             self.enabled = False
             w = self.worker
             w.pipeline._step_open = False

@@ -211,12 +211,15 @@ def _norm_accepts_fp32_stats(device: torch.device) -> bool:
     key = str(device)
     if key not in _NORM_FP32_STATS:
         try:
-            x = torch.randn(4, 3, 2, 2, device=device).to(torch.bfloat16)
-            w = torch.ones(3, device=device, dtype=torch.bfloat16)
-            b = torch.zeros(3, device=device, dtype=torch.bfloat16)
+            x = torch.randn(4, 3, 2, 2, device=device).to(torch.bfloat16).requires_grad_(True)
+            w = torch.ones(3, device=device, dtype=torch.bfloat16, requires_grad=True)
+            b = torch.zeros(3, device=device, dtype=torch.bfloat16, requires_grad=True)
             rm, rv = torch.zeros(3, device=device), torch.ones(3, device=device)
-            torch.nn.functional.batch_norm(x, rm, rv, w, b, training=True)
-            torch.nn.functional.batch_norm(x, rm, rv, w, b, training=False)
+            with torch.enable_grad():
+                # forward AND backward (torch 2.11's batch_norm backward insists on statistics of
+                # the affine parameters' dtype although its forward does not)
+                torch.nn.functional.batch_norm(x, rm, rv, w, b, training=True).float().sum().backward()
+                torch.nn.functional.batch_norm(x, rm, rv, w, b, training=False).float().sum().backward()
             ok = bool(rm.abs().sum() > 0) and rm.dtype == torch.float32
         except Exception as e:                       # noqa: BLE001
             logger.info("fp32 BatchNorm statistics next to bf16 parameters are not supported here (%s): "
