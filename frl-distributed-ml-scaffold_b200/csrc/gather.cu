@@ -5,15 +5,18 @@
 // transform.py:25-38).  Here the raw dataset stays in pinned host memory and the GPU pulls the
 // rows of the batch itself: dst[i, :] = src[idx[i], :].  The PCIe reads ARE the host->device
 // transfer, there is no host-side gather, collate or staging copy.
-// One CTA walks (row, 4 KB segment) pairs; every thread keeps four independent 16-byte reads in
-// flight, which is what hides the ~2 us PCIe round trip.
+// The batch is walked as a flat array of 16-byte units (unit u lives in batch row u / units_per_row),
+// so short rows (an 8 KB bf16 feature row) fill a CTA pass as well as long ones; every thread keeps
+// kGUnroll independent 16-byte reads in flight — 32 KB per CTA — which is what hides the ~2 us PCIe
+// round trip with only a handful of CTAs (55 GB/s x 2 us = 110 KB in flight for the whole GPU): the
+// fewer SMs this kernel occupies for the ~0.6 ms a batch takes, the less the training step's GEMMs
+// running beside it lose.
 #include "frl_common.cuh"
 
 namespace frl {
 
 constexpr int kGThreads = 256;
-constexpr int kGUnroll = 4;
-constexpr int64_t kGSegBytes = static_cast<int64_t>(kGThreads) * kGUnroll * 16;   // 16 KB per CTA pass
+constexpr int kGUnroll = 8;
 
 __device__ __forceinline__ int4 ld_host16(const int4* p) {
     int4 r;
@@ -22,29 +25,33 @@ __device__ __forceinline__ int4 ld_host16(const int4* p) {
     return r;
 }
 
+// IDX = uint32_t when the batch has fewer than 2^32 units (one 32-bit division per unit), else int64_t
+template <typename IDX>
 __global__ void __launch_bounds__(kGThreads)
 gather_rows_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ idx,
                    uint8_t* __restrict__ dst, int64_t n_rows, int64_t row_bytes, int64_t src_rows) {
-    const int64_t segs_per_row = (row_bytes + kGSegBytes - 1) / kGSegBytes;
-    const int64_t total = n_rows * segs_per_row;
-    for (int64_t work = blockIdx.x; work < total; work += gridDim.x) {
-        const int64_t row = work / segs_per_row, seg = work % segs_per_row;
-        int64_t from = __ldg(idx + row);
-        if (from < 0 || from >= src_rows) from = 0;            // never read outside the dataset
-        const int64_t base = seg * kGSegBytes;
-        const int4* s = reinterpret_cast<const int4*>(src + from * row_bytes + base);
-        int4* d = reinterpret_cast<int4*>(dst + row * row_bytes + base);
-        const int64_t n16 = ((row_bytes - base < kGSegBytes ? row_bytes - base : kGSegBytes)) >> 4;
+    const IDX upr = static_cast<IDX>(row_bytes >> 4);                 // 16-byte units per row
+    const int64_t total = n_rows * static_cast<int64_t>(upr);
+    const int64_t per_pass = static_cast<int64_t>(kGThreads) * kGUnroll;
+    const int4* s16 = reinterpret_cast<const int4*>(src);
+    int4* d16 = reinterpret_cast<int4*>(dst);
+    for (int64_t base = blockIdx.x * per_pass; base < total; base += gridDim.x * per_pass) {
         int4 v[kGUnroll];
 #pragma unroll
-        for (int u = 0; u < kGUnroll; ++u) {
-            const int64_t i = threadIdx.x + static_cast<int64_t>(u) * kGThreads;
-            if (i < n16) v[u] = ld_host16(s + i);
+        for (int k = 0; k < kGUnroll; ++k) {
+            const int64_t u = base + threadIdx.x + static_cast<int64_t>(k) * kGThreads;
+            if (u < total) {
+                const IDX row = static_cast<IDX>(u) / upr;
+                const IDX col = static_cast<IDX>(u) - row * upr;
+                int64_t from = __ldg(idx + row);
+                if (from < 0 || from >= src_rows) from = 0;            // never read outside the dataset
+                v[k] = ld_host16(s16 + from * static_cast<int64_t>(upr) + col);
+            }
         }
 #pragma unroll
-        for (int u = 0; u < kGUnroll; ++u) {
-            const int64_t i = threadIdx.x + static_cast<int64_t>(u) * kGThreads;
-            if (i < n16) d[i] = v[u];
+        for (int k = 0; k < kGUnroll; ++k) {
+            const int64_t u = base + threadIdx.x + static_cast<int64_t>(k) * kGThreads;
+            if (u < total) d16[u] = v[k];
         }
     }
 }
@@ -185,12 +192,18 @@ extern "C" int frl_gather_rows(const void* src_mapped, int64_t src_rows, const i
             launch_small<uint8_t>(src_mapped, idx_dev, dst, n_rows, row_bytes, src_rows, max_blocks, st);
         return after_launch("frl_gather_rows");
     }
-    const int64_t segs = n_rows * ((row_bytes + kGSegBytes - 1) / kGSegBytes);
+    const int64_t units = n_rows * (row_bytes >> 4);
+    const int64_t passes = (units + static_cast<int64_t>(kGThreads) * kGUnroll - 1) / (static_cast<int64_t>(kGThreads) * kGUnroll);
     int64_t grid = max_blocks > 0 ? max_blocks : 64;
-    if (grid > segs) grid = segs;
-    gather_rows_kernel<<<static_cast<int>(grid), kGThreads, 0, st>>>(
-        static_cast<const uint8_t*>(src_mapped), idx_dev, static_cast<uint8_t*>(dst), n_rows, row_bytes,
-        src_rows);
+    if (grid > passes) grid = passes;
+    if (units < (1ll << 32) && (row_bytes >> 4) < (1ll << 31))
+        gather_rows_kernel<uint32_t><<<static_cast<int>(grid), kGThreads, 0, st>>>(
+            static_cast<const uint8_t*>(src_mapped), idx_dev, static_cast<uint8_t*>(dst), n_rows, row_bytes,
+            src_rows);
+    else
+        gather_rows_kernel<int64_t><<<static_cast<int>(grid), kGThreads, 0, st>>>(
+            static_cast<const uint8_t*>(src_mapped), idx_dev, static_cast<uint8_t*>(dst), n_rows, row_bytes,
+            src_rows);
     return after_launch("frl_gather_rows");
 }
 

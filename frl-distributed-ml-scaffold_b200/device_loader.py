@@ -140,7 +140,9 @@ class DeviceBatchLoader:
                              "CPU memory (use the host path)" % self.path)
         if self.path not in ("host", "tma", "kernel"):
             raise ValueError(f"unknown input path {self.path!r}")
-        self.blocks = int(os.environ.get("FRL_B200_INPUT_BLOCKS", "2" if self.path == "tma" else "16"))
+        # CTAs of the GPU-pulled paths: each LSU CTA keeps 32 KB of PCIe reads in flight, 8 of them
+        # cover the ~110 KB the link needs; more only take SMs from the step's GEMMs
+        self.blocks = int(os.environ.get("FRL_B200_INPUT_BLOCKS", "2" if self.path == "tma" else "8"))
         # wire dtype per field: fp32 fields the dataset's transform declares bf16-tolerant
         # (``bf16_wire_fields``) travel over PCIe as bf16 when the run computes in bf16 — half the
         # bytes of the step's dominant transfer.  FRL_B200_INPUT_WIRE: "auto" (default: do it),
@@ -217,7 +219,12 @@ class DeviceBatchLoader:
             seed = int(torch.empty((), dtype=torch.int64).random_().item())   # RandomSampler.__iter__
             gen = torch.Generator()
             gen.manual_seed(seed)
+            import time as _time
+            t0 = _time.perf_counter()
             perm = torch.randperm(len(sampler.data_source), generator=gen)
+            if os.environ.get("FRL_B200_EPOCH_TRACE"):
+                print("loader trace: randperm(%d) %.2f ms" % (perm.numel(), 1e3 * (_time.perf_counter() - t0)),
+                      flush=True, file=__import__("sys").stderr)
         elif hasattr(sampler, "rank_index_tensor"):                       # ScaffoldSampler
             torch.empty((), dtype=torch.int64).random_()                  # DataLoader iterator: _base_seed
             perm = sampler.rank_index_tensor()

@@ -16,6 +16,7 @@ host with the device:
 * one watchdog thread per split is kicked per step instead of spawning a Timer per step.
 """
 import bisect
+from contextlib import contextmanager
 import heapq
 import io
 import os
@@ -542,6 +543,20 @@ def _planned_order(sampler, accessor) -> List[int]:
     return list(iter(sampler))
 
 
+@contextmanager
+def _gc_paused():
+    """Cyclic GC off for the duration (unless FRL_B200_GC_IN_LOOP=1), restored on any exit."""
+    import gc
+    pause = gc.isenabled() and os.environ.get("FRL_B200_GC_IN_LOOP", "0") == "0"
+    if pause:
+        gc.disable()
+    try:
+        yield
+    finally:
+        if pause:
+            gc.enable()
+
+
 class SolverWorker:
     def __init__(self, model: torch.nn.Module, criterion: BaseParallelCriterion,
                  optimizer: FusedArenaOptimizer, device: torch.device, run_opts: RunOpts,
@@ -631,7 +646,13 @@ class SolverWorker:
             batch_start = time.time()
             mark("setup done")
 
-            with StepWatchdog(self.run_opts.minibatchTimeoutMs) as dog, sampler_state:
+            # The cyclic garbage collector stays out of the minibatch loop: a generation-2 pass over
+            # a process holding a model, an optimizer and a loader takes 5-10 ms — a handful of B200
+            # steps — and fires wherever the allocation counter happens to trip (measured: the first
+            # batch of an epoch served 1 to 13 ms late).  A step leaves no reference cycles behind
+            # (its autograd graph is dropped explicitly below); FRL_B200_GC_IN_LOOP=1 keeps the
+            # collector on for Problems whose hooks do.
+            with StepWatchdog(self.run_opts.minibatchTimeoutMs) as dog, sampler_state, _gc_paused():
                 for minibatch_idx, (data, target, raw_meta) in enumerate(loader):
                     dog.kick()
                     if minibatch_idx < 3:
