@@ -54,10 +54,16 @@ class ParamArena:
     def __init__(self, model_params: Iterable[nn.Parameter],
                  criterion_params: Iterable[nn.Parameter] = (),
                  *, device: torch.device, precision: Precision = Precision.FP32,
-                 shared_allocator=None) -> None:
+                 shared_allocator=None, adjacent: Sequence[Sequence[nn.Parameter]] = ()) -> None:
         """``shared_allocator(numel, dtype) -> zeroed tensor``: where the vectors other ranks must
         reach (``grad`` and the weights the modules read) come from — symmetric/multicast memory
-        for the fused NVLS step; default ``torch.zeros``."""
+        for the fused NVLS step; default ``torch.zeros``.
+
+        ``adjacent``: groups of model parameters to lay out back to back, in the given order,
+        where the first member would have gone (e.g. the weights of all task heads, so that one
+        GEMM can treat them as a single [sum(C_i), K] matrix).  A group is honoured only if every
+        member but the last has a multiple of 8 elements (no padding in between); the slot list
+        stays sorted by offset, ``ArenaSlot.index`` keeps the optimizer's parameter position."""
         self.device = torch.device(device)
         self.precision = precision
         self.all_params: List[nn.Parameter] = []
@@ -66,13 +72,41 @@ class ParamArena:
         off = 0
         model_params = list(model_params)
         criterion_params = list(criterion_params)
-        for is_model, group in ((True, model_params), (False, criterion_params)):
+        # optimizer positions follow the reference's parameter order, whatever the layout
+        position, uniq = {}, []
+        for p in model_params + criterion_params:
+            if id(p) not in position:
+                position[id(p)] = len(uniq)
+                uniq.append(p)
+        self.all_params = uniq
+        model_ids = {id(p) for p in model_params}
+        lead = {}                                     # id(first member) -> whole group
+        grouped = set()
+        self.adjacent_groups: List[List[nn.Parameter]] = []
+        for group in adjacent:
+            group = list(group)
+            ok = (len(group) >= 2 and all(id(p) in model_ids and p.requires_grad for p in group)
+                  and len({id(p) for p in group}) == len(group)
+                  and not any(id(p) in grouped for p in group)
+                  and all(p.numel() % ALIGN_ELEMS == 0 for p in group[:-1]))
+            if ok:
+                lead[id(group[0])] = group
+                grouped.update(id(p) for p in group)
+                self.adjacent_groups.append(group)
+
+        def laid_out(params):
+            for p in params:
+                if id(p) in lead:
+                    yield from lead[id(p)]
+                elif id(p) not in grouped:
+                    yield p
+
+        for is_model, group in ((True, list(laid_out(model_params))), (False, criterion_params)):
             for p in group:
                 if id(p) in seen:
                     continue
                 seen.add(id(p))
-                idx = len(self.all_params)
-                self.all_params.append(p)
+                idx = position[id(p)]
                 if not p.requires_grad:
                     continue
                 if p.dtype != torch.float32:

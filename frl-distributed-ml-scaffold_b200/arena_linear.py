@@ -131,6 +131,119 @@ class _ArenaLinearReluFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class _ArenaMultiHeadFn(torch.autograd.Function):
+    """All task heads of a ``MultiTaskModel`` (exact ``nn.Linear`` layers on the same trunk
+    output) as one autograd unit.  Forward: one GEMM per head, as before (their outputs are
+    separate tensors for the criterion).  Backward: the heads' weights lie back to back in the
+    arena (``ParamArena(adjacent=...)``), so with dY = [dY_1 | ... | dY_T]
+
+        dX   = dY W_cat            ONE GEMM instead of T GEMMs and T-1 accumulate passes
+        dW   = dY^T X              ONE GEMM writing every head's weight gradient in place
+        db   = colsum(dY)          ONE launch when the biases are adjacent too, else one per head
+    """
+
+    @staticmethod
+    def forward(ctx, x, site, *params):
+        ctx.site = site
+        ctx.save_for_backward(x)
+        ctx.n_heads = len(params) // 2
+        return tuple(F.linear(x, params[2 * i], params[2 * i + 1]) for i in range(ctx.n_heads))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *dys):
+        (x,) = ctx.saved_tensors
+        site = ctx.site
+        pipe = site.pipeline
+        dy = torch.cat(dys, dim=1)
+        dx = dy.matmul(site.weight_cat()) if ctx.needs_input_grad[0] else None
+        none = (None,) * (2 * ctx.n_heads)
+        if pipe is not None and pipe.step_open:
+            gw = site.grad_weight_cat()
+            if site.heads[0].wstate.first_touch(pipe.step_id):
+                torch.mm(dy.t(), x, out=gw)
+            else:
+                gw.addmm_(dy.t(), x)
+            for h in site.heads[1:]:
+                h.wstate.first_touch(pipe.step_id)
+            gb = site.grad_bias_cat()
+            if gb is not None:
+                first = site.heads[0].bstate.first_touch(pipe.step_id)
+                for h in site.heads[1:]:
+                    h.bstate.first_touch(pipe.step_id)
+                KERNELS.colsum(dy, gb, accumulate=not first)
+            else:
+                for h, dyi in zip(site.heads, dys):
+                    KERNELS.colsum(dyi.contiguous(), pipe.arena.grad_view(h.bslot),
+                                   accumulate=not h.bstate.first_touch(pipe.step_id))
+            for h in site.heads:
+                h.backward_done(pipe)
+            return (dx, None) + none
+        grads = []
+        for i, dyi in enumerate(dys):
+            grads += [dyi.t().mm(x) if ctx.needs_input_grad[2 + 2 * i] else None,
+                      dyi.sum(0) if ctx.needs_input_grad[3 + 2 * i] else None]
+        return (dx, None) + tuple(grads)
+
+
+class MultiHeadSite:
+    """The task heads of one ``MultiTaskModel`` whose weights (and, if their sizes allow, biases)
+    are adjacent in the arena."""
+
+    def __init__(self, model, heads: List["LinearSite"], pipeline) -> None:
+        self.model = model
+        self.heads = heads
+        self.pipeline = pipeline
+        arena = pipeline.arena
+        self.rows = sum(h.module.out_features for h in heads)
+        self.cols = heads[0].module.in_features
+        self._w_lo = heads[0].wslot.offset
+        ends = [h.wslot.end for h in heads]
+        starts = [h.wslot.offset for h in heads]
+        assert all(e == s for e, s in zip(ends[:-1], starts[1:])), "head weights are not adjacent"
+        self._w_hi = ends[-1]
+        b_adjacent = all(h.bslot.end == n.bslot.offset for h, n in zip(heads[:-1], heads[1:]))
+        self._b = (heads[0].bslot.offset, heads[-1].bslot.end) if b_adjacent else None
+        self._arena = arena
+
+    def weight_cat(self) -> torch.Tensor:
+        a = self._arena
+        store = a.lp if self.heads[0].wslot.uses_lp else a.master
+        return store[self._w_lo:self._w_hi].view(self.rows, self.cols)
+
+    def grad_weight_cat(self) -> torch.Tensor:
+        return self._arena.grad[self._w_lo:self._w_hi].view(self.rows, self.cols)
+
+    def grad_bias_cat(self) -> Optional[torch.Tensor]:
+        return None if self._b is None else self._arena.grad[self._b[0]:self._b[1]]
+
+
+def head_layout_groups(model: nn.Module) -> List[List[nn.Parameter]]:
+    """Parameter groups ``ParamArena(adjacent=...)`` should lay out back to back so the heads of a
+    ``MultiTaskModel`` can run as one backward unit: [all head weights], [all head biases]."""
+    from .model import MultiTaskModel
+    if type(model) is not MultiTaskModel or os.environ.get("FRL_B200_FUSE_HEADS", "1") == "0":
+        return []
+    heads = list(model.additional_layers)
+    if len(heads) < 2 or any(type(h) is not nn.Linear or h.bias is None for h in heads):
+        return []
+    if len({h.in_features for h in heads}) != 1 or len({id(h.weight) for h in heads}) != len(heads):
+        return []
+    return [[h.weight for h in heads], [h.bias for h in heads]]
+
+
+def _multihead_forward(self, x):
+    site = self._frl_heads
+    shared = self.model_base(x)
+    if shared.dim() == 2 and torch.is_grad_enabled() and shared.is_contiguous():
+        params = []
+        for h in site.heads:
+            h.count_forward()
+            params += [h.module.weight, h.module.bias]
+        return list(_ArenaMultiHeadFn.apply(shared, site, *params))
+    return [head(shared) for head in self.additional_layers]
+
+
 class SlotState:
     """Per-PARAMETER bookkeeping shared by every site that uses the parameter (a module applied
     several times per forward, or weights tied across modules): which step first wrote the
@@ -172,7 +285,7 @@ class LinearSite:
     site counts its applications in the forward pass (training mode, autograd on) and marks its
     slots ready only when as many backward passes have run; anything left over is marked by
     ``GradBucketPipeline.finish_step`` (after ``backward()`` returned nothing can be missing)."""
-    __slots__ = ("module", "wslot", "bslot", "pipeline", "relu", "wstate", "bstate")
+    __slots__ = ("module", "wslot", "bslot", "pipeline", "relu", "wstate", "bstate", "multihead")
 
     def __init__(self, module, wslot, bslot, pipeline):
         self.module = module
@@ -180,6 +293,7 @@ class LinearSite:
         self.bslot = bslot
         self.pipeline = pipeline
         self.relu = None              # the nn.ReLU this layer absorbed (FRL_B200_FUSE_RELU)
+        self.multihead = None         # on the first head: the MultiHeadSite of its model
         states = pipeline.slot_states
         self.wstate = states.setdefault(wslot.index, SlotState())
         self.bstate = states.setdefault(bslot.index, SlotState()) if bslot is not None else None
@@ -266,8 +380,30 @@ def patch_linears(model: nn.Module, pipeline) -> List[LinearSite]:
         sites.append(site)
     if os.environ.get("FRL_B200_FUSE_RELU", "1") != "0":
         _fuse_relu_pairs(model, sites)
+    _attach_multihead(model, sites, pipeline)
     repatch_linears(sites)
     return sites
+
+
+def _attach_multihead(model: nn.Module, sites: List[LinearSite], pipeline) -> None:
+    """Run the heads as one backward unit if the arena laid their weights out adjacently."""
+    groups = head_layout_groups(model)
+    if not groups or "forward" in model.__dict__ or _has_hooks(model):
+        return
+    by_module = {id(s.module): s for s in sites}
+    heads = [by_module.get(id(h)) for h in model.additional_layers]
+    if any(h is None or h.relu is not None or h.bslot is None for h in heads):
+        return
+    if any(a.wslot.end != b.wslot.offset for a, b in zip(heads[:-1], heads[1:])):
+        return                                   # the arena did not honour the weight group
+    uses = Counter(id(child) for mod in model.modules() for child in mod._modules.values()
+                   if child is not None)
+    if any(uses[id(h.module)] != 1 or _has_hooks(h.module) for h in heads):
+        return
+    msite = MultiHeadSite(model, heads, pipeline)
+    for s in sites:
+        if s is heads[0]:
+            s.multihead = msite
 
 
 def unpatch_linears(sites: List[LinearSite]) -> None:
@@ -276,6 +412,9 @@ def unpatch_linears(sites: List[LinearSite]) -> None:
         site.module.__dict__.pop("_frl_site", None)
         if site.relu is not None:
             site.relu.__dict__.pop("forward", None)
+        if site.multihead is not None:
+            site.multihead.model.__dict__.pop("forward", None)
+            site.multihead.model.__dict__.pop("_frl_heads", None)
 
 
 def repatch_linears(sites: List[LinearSite]) -> None:
@@ -286,3 +425,6 @@ def repatch_linears(sites: List[LinearSite]) -> None:
             site.relu.forward = types.MethodType(_identity, site.relu)
         else:
             site.module.forward = types.MethodType(_forward, site.module)
+        if site.multihead is not None:
+            site.multihead.model._frl_heads = site.multihead
+            site.multihead.model.forward = types.MethodType(_multihead_forward, site.multihead.model)

@@ -34,6 +34,26 @@ template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bflo
     v[0] = bf16lo(r.a); v[1] = bf16hi(r.a); v[2] = bf16lo(r.b); v[3] = bf16hi(r.b);
     v[4] = bf16lo(r.c); v[5] = bf16hi(r.c); v[6] = bf16lo(r.d); v[7] = bf16hi(r.d);
 }
+// raw 8-element vectors: loaded first (all rows of a trip), unpacked only afterwards — a warp issues
+// in order, so an unpack placed between two loads would make the second load wait for the first
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { f32x4 a, b; };
+template <> struct Raw8<__nv_bfloat16> { bf16x8 r; };
+__device__ __forceinline__ void load_raw8(const float* p, Raw8<float>& q) {
+    q.a = ld_stream_ro(reinterpret_cast<const f32x4*>(p));
+    q.b = ld_stream_ro(reinterpret_cast<const f32x4*>(p) + 1);
+}
+__device__ __forceinline__ void load_raw8(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& q) {
+    q.r = ld_stream_ro(reinterpret_cast<const bf16x8*>(p));
+}
+__device__ __forceinline__ void unpack8(const Raw8<float>& q, float (&v)[8]) {
+    v[0] = q.a.x; v[1] = q.a.y; v[2] = q.a.z; v[3] = q.a.w; v[4] = q.b.x; v[5] = q.b.y; v[6] = q.b.z; v[7] = q.b.w;
+}
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& q, float (&v)[8]) {
+    v[0] = bf16lo(q.r.a); v[1] = bf16hi(q.r.a); v[2] = bf16lo(q.r.b); v[3] = bf16hi(q.r.b);
+    v[4] = bf16lo(q.r.c); v[5] = bf16hi(q.r.c); v[6] = bf16lo(q.r.d); v[7] = bf16hi(q.r.d);
+}
+
 template <typename T> __device__ __forceinline__ float ld1(const T* p);
 template <> __device__ __forceinline__ float ld1<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float ld1<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
@@ -56,7 +76,7 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
 // to `dz` on the way and the column sums are those of dZ — ReLU's backward and the bias-gradient
 // reduction in the one pass over dY that the reduction needs anyway.
 template <typename XT, typename OT, bool VEC, bool MASK, int kSRowsInFlight>
-__global__ void __launch_bounds__(kSThreads)
+__global__ void __launch_bounds__(kSThreads, 4)
 colsum_kernel(const XT* __restrict__ x, const XT* __restrict__ act, XT* __restrict__ dz, int64_t rows,
               int64_t cols, OT* __restrict__ out,
               int accumulate, unsigned int* __restrict__ tickets, float* __restrict__ partial) {
@@ -76,26 +96,30 @@ colsum_kernel(const XT* __restrict__ x, const XT* __restrict__ act, XT* __restri
             const int64_t rstep = static_cast<int64_t>(nsplit) * kSWarps;
             for (int64_t r0 = static_cast<int64_t>(split) * kSWarps + warp; r0 < rows;
                  r0 += rstep * kSRowsInFlight) {
-                float v[kSRowsInFlight][8], a[kSRowsInFlight][8];
+                Raw8<XT> qv[kSRowsInFlight], qa[kSRowsInFlight];
 #pragma unroll
                 for (int u = 0; u < kSRowsInFlight; ++u) {
                     const int64_t r = r0 + u * rstep;
                     if (r < rows) {
-                        load8<XT>(x + r * cols + c0, v[u]);
-                        if (MASK) load8<XT>(act + r * cols + c0, a[u]);
+                        load_raw8(x + r * cols + c0, qv[u]);
+                        if (MASK) load_raw8(act + r * cols + c0, qa[u]);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < kSRowsInFlight; ++u) {
                     const int64_t r = r0 + u * rstep;
                     if (r >= rows) break;
+                    float v[8];
+                    unpack8(qv[u], v);
                     if (MASK) {
+                        float a[8];
+                        unpack8(qa[u], a);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[u][k] = a[u][k] > 0.f ? v[u][k] : 0.f;
-                        store8<XT>(dz + r * cols + c0, v[u]);
+                        for (int k = 0; k < 8; ++k) v[k] = a[k] > 0.f ? v[k] : 0.f;
+                        store8<XT>(dz + r * cols + c0, v);
                     }
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[k] += v[u][k];
+                    for (int k = 0; k < 8; ++k) acc[k] += v[k];
                 }
             }
         }
@@ -182,7 +206,7 @@ static int launch_colsum(const void* x, const void* act, void* dz, int x_dtype, 
     const bool vec = (cols % 8 == 0) && aligned16(x) && (!mask || (aligned16(act) && aligned16(dz)));
     static const int rows_in_flight = [] {
         const char* e = getenv("FRL_B200_COLSUM_ROWS");       // tuning knob: rows a warp keeps in flight
-        return e ? atoi(e) : 1;
+        return e ? atoi(e) : 0;       // 0 = auto: 4 rows (plain), 2 rows (with the activation: 2 loads per row)
     }();
     dim3 grid(static_cast<unsigned int>(tiles), static_cast<unsigned int>(splits));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -192,8 +216,9 @@ static int launch_colsum(const void* x, const void* act, void* dz, int x_dtype, 
         static_cast<OT*>(out), accumulate, tickets, partial)
 #define FRL_CS2(XT, OT, V, M)                                                                        \
     do {                                                                                             \
-        if (rows_in_flight >= 4) FRL_CS3(XT, OT, V, M, 4);                                           \
-        else if (rows_in_flight == 2) FRL_CS3(XT, OT, V, M, 2);                                      \
+        const int rif = rows_in_flight > 0 ? rows_in_flight : ((M) ? 2 : 4);                         \
+        if (rif >= 4) FRL_CS3(XT, OT, V, M, 4);                                                      \
+        else if (rif == 2) FRL_CS3(XT, OT, V, M, 2);                                                 \
         else FRL_CS3(XT, OT, V, M, 1);                                                               \
     } while (0)
 #define FRL_CS(XT, OT)                                                                               \

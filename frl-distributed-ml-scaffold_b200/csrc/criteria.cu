@@ -27,6 +27,7 @@ constexpr int kCRowChunk = 32 * 4 * kCVecPerLane;   // 1024 columns: one registe
 struct CritParams {
     frl_task_desc t[FRL_MAX_TASKS];
     int nblk[FRL_MAX_TASKS];        // CTAs working on task i
+    int blk_start[FRL_MAX_TASKS];   // first CTA (of the 1-D grid) of task i
     int part_off[FRL_MAX_TASKS];    // first partial slot of task i
     int64_t lse_off[FRL_MAX_TASKS]; // offset of task i's rows in the lse array (CE only)
     int n_tasks;
@@ -79,6 +80,25 @@ template <> __device__ __forceinline__ void st4<__nv_bfloat16>(void* base, int64
         bf16x4{pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)};
 }
 
+// a row chunk is held in registers in its STORAGE type (bf16: 2 registers per 4 logits) and
+// converted on each use: 16 instead of 32 registers for a 1024-column row, which is what lets
+// every CTA of a [4096, 1000] criterion be resident at once (one wave)
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { f32x4 v; };
+template <> struct Raw4<__nv_bfloat16> { bf16x4 v; };
+__device__ __forceinline__ Raw4<float> ldraw4(const float* base, int64_t e) {
+    return Raw4<float>{*reinterpret_cast<const f32x4*>(base + e)};
+}
+__device__ __forceinline__ Raw4<__nv_bfloat16> ldraw4(const __nv_bfloat16* base, int64_t e) {
+    return Raw4<__nv_bfloat16>{*reinterpret_cast<const bf16x4*>(base + e)};
+}
+__device__ __forceinline__ f32x4 cvt4(const Raw4<float>& r) { return r.v; }
+__device__ __forceinline__ f32x4 cvt4(const Raw4<__nv_bfloat16>& r) {
+    return f32x4{bf16lo(r.v.a), bf16hi(r.v.a), bf16lo(r.v.b), bf16hi(r.v.b)};
+}
+__device__ __forceinline__ void fill_neg_inf(Raw4<float>& r) { r.v = f32x4{-INFINITY, -INFINITY, -INFINITY, -INFINITY}; }
+__device__ __forceinline__ void fill_neg_inf(Raw4<__nv_bfloat16>& r) { r.v = bf16x4{0xff80ff80u, 0xff80ff80u}; }
+
 __device__ __forceinline__ bool vec_ok(const frl_task_desc& t) {
     const int esz = t.out_dtype == FRL_F32 ? 4 : 2;
     return (t.cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(t.out) % (4 * esz)) == 0) &&
@@ -121,21 +141,25 @@ __device__ __forceinline__ void ce_partial(const frl_task_desc& t, int blk, int 
             // the whole row in registers: every lane issues its (up to) 8 loads back to back, one
             // trip to memory per row; max and sum(exp) are then formed exactly as in the two-pass
             // form (max over the row first, then exp(x - max))
-            f32x4 v[kCVecPerLane];
+            Raw4<OT> q[kCVecPerLane];
+            const OT* base = static_cast<const OT*>(t.out);
 #pragma unroll
             for (int j = 0; j < kCVecPerLane; ++j) {
                 const int64_t c = lane * 4 + j * 128;
-                v[j] = c < C ? ld4<OT>(t.out, r0 + c) : f32x4{-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                if (c < C) q[j] = ldraw4(base, r0 + c); else fill_neg_inf(q[j]);
             }
 #pragma unroll
-            for (int j = 0; j < kCVecPerLane; ++j)
-                m = fmaxf(fmaxf(m, fmaxf(v[j].x, v[j].y)), fmaxf(v[j].z, v[j].w));
+            for (int j = 0; j < kCVecPerLane; ++j) {
+                const f32x4 v = cvt4(q[j]);
+                m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+            }
             m = warp_max(m);
 #pragma unroll
             for (int j = 0; j < kCVecPerLane; ++j) {
                 if (lane * 4 + j * 128 < C) {
-                    has_nan |= (v[j].x != v[j].x) | (v[j].y != v[j].y) | (v[j].z != v[j].z) | (v[j].w != v[j].w);
-                    se += expf(v[j].x - m) + expf(v[j].y - m) + expf(v[j].z - m) + expf(v[j].w - m);
+                    const f32x4 v = cvt4(q[j]);
+                    has_nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+                    se += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
                 }
             }
         } else if (vec) {
@@ -199,16 +223,18 @@ __device__ __forceinline__ void ce_partial(const frl_task_desc& t, int blk, int 
     nvalid = s_valid;
 }
 
-__global__ void __launch_bounds__(kCThreads)
+__global__ void __launch_bounds__(kCThreads, 5)
 criteria_fwd_kernel(const __grid_constant__ CritParams P, float* __restrict__ losses,
                     float* __restrict__ aux, float* __restrict__ lse,
                     float* __restrict__ sink, int32_t* __restrict__ nan_flag,
                     CritScratchHeader* __restrict__ hdr) {
     __shared__ float smem[32];
     __shared__ bool is_last;
-    const int ti = blockIdx.y;
-    const int blk = blockIdx.x;
-    if (blk >= P.nblk[ti]) return;
+    int ti = 0;
+#pragma unroll
+    for (int i = 1; i < FRL_MAX_TASKS; ++i)
+        if (i < P.n_tasks && static_cast<int>(blockIdx.x) >= P.blk_start[i]) ti = i;
+    const int blk = static_cast<int>(blockIdx.x) - P.blk_start[ti];
     const frl_task_desc& t = P.t[ti];
     const int npart = P.n_tasks * kCMaxBlocksPerTask;
     float* part_sum = reinterpret_cast<float*>(hdr + 1);
@@ -347,12 +373,14 @@ __device__ __forceinline__ void ce_bwd(const frl_task_desc& t, int blk, int nblk
     }
 }
 
-__global__ void __launch_bounds__(kCThreads)
+__global__ void __launch_bounds__(kCThreads, 5)
 criteria_bwd_kernel(const __grid_constant__ CritParams P, const float* __restrict__ gl,
                     const float* __restrict__ aux, const float* __restrict__ lse) {
-    const int ti = blockIdx.y;
-    const int blk = blockIdx.x;
-    if (blk >= P.nblk[ti]) return;
+    int ti = 0;
+#pragma unroll
+    for (int i = 1; i < FRL_MAX_TASKS; ++i)
+        if (i < P.n_tasks && static_cast<int>(blockIdx.x) >= P.blk_start[i]) ti = i;
+    const int blk = static_cast<int>(blockIdx.x) - P.blk_start[ti];
     const frl_task_desc& t = P.t[ti];
     const float scale = (__ldg(gl) + __ldg(gl + 1 + ti)) * t.weight * __ldg(aux + ti);
     if (t.kind == FRL_LOSS_MSE) {
@@ -390,7 +418,7 @@ static int build_params(const frl_task_desc* tasks, int T, bool backward, CritPa
         }
         P.t[i] = t;
         int64_t work_blocks;
-        if (t.kind == FRL_LOSS_MSE) work_blocks = (t.rows * t.cols + kCThreads * 4 - 1) / (kCThreads * 4);
+        if (t.kind == FRL_LOSS_MSE) work_blocks = (t.rows * t.cols + kCThreads * 8 - 1) / (kCThreads * 8);
         else                        work_blocks = (t.rows + kCWarps - 1) / kCWarps;
         if (work_blocks < 1) work_blocks = 1;
         if (work_blocks > kCMaxBlocksPerTask) work_blocks = kCMaxBlocksPerTask;
@@ -402,7 +430,10 @@ static int build_params(const frl_task_desc* tasks, int T, bool backward, CritPa
         if (P.nblk[i] > max_blk) max_blk = P.nblk[i];
     }
     int total = 0;
-    for (int i = 0; i < T; ++i) total += P.nblk[i];
+    for (int i = 0; i < T; ++i) {
+        P.blk_start[i] = total;
+        total += P.nblk[i];
+    }
     P.total_blocks = total;
     return 0;
 }
@@ -427,7 +458,7 @@ extern "C" int frl_criteria_forward(const frl_task_desc* tasks_host, int n_tasks
     bool any_ce = false;
     for (int i = 0; i < n_tasks; ++i) any_ce |= (tasks_host[i].kind == FRL_LOSS_CE);
     FRL_REQUIRE(!any_ce || lse, FRL_E_ARG, "frl_criteria_forward: CE task needs lse buffer");
-    dim3 grid(max_blk, n_tasks);
+    const int grid = P.total_blocks;        // one CTA per unit of work: no empty CTAs, one wave
     criteria_fwd_kernel<<<grid, kCThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         P, losses, aux, lse, sink_mapped, nan_flag_mapped, static_cast<CritScratchHeader*>(scratch));
     return after_launch("frl_criteria_forward");
@@ -441,7 +472,7 @@ extern "C" int frl_criteria_backward(const frl_task_desc* tasks_host, int n_task
     const int rc = build_params(tasks_host, n_tasks, true, P, max_blk, "frl_criteria_backward");
     if (rc) return rc;
     FRL_REQUIRE(grad_losses && aux, FRL_E_ARG, "frl_criteria_backward: null inputs");
-    dim3 grid(max_blk, n_tasks);
+    const int grid = P.total_blocks;
     criteria_bwd_kernel<<<grid, kCThreads, 0, static_cast<cudaStream_t>(stream)>>>(P, grad_losses, aux, lse);
     return after_launch("frl_criteria_backward");
 }

@@ -184,7 +184,7 @@ class FusedArenaOptimizer(torch.optim.Optimizer):
     def state_dict(self) -> Dict[str, Any]:
         state: Dict[int, Dict[str, Any]] = {}
         if self._steps > 0:
-            for s in self.arena.slots:
+            for s in sorted(self.arena.slots, key=lambda s: s.index):     # torch's key order
                 entry = dict(self._per_param_extra())
                 for torch_name, vec_name in self.STATE_NAMES:
                     if vec_name in self._vec:

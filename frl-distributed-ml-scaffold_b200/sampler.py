@@ -54,7 +54,8 @@ class ScaffoldSampler(torch.utils.data.distributed.DistributedSampler):
             return order[self.rank % ranks_per_node:: ranks_per_node].contiguous()
         if self._shuffle_type != ShuffleType.RANDPERM:
             raise ValueError("Unhandled shuffle type %s", self._shuffle_type)
-        order = torch.randperm(n, generator=gen) if self.shuffle else torch.arange(n)
+        from .device_loader import randperm_quiet
+        order = randperm_quiet(n, gen) if self.shuffle else torch.arange(n)
         order = torch.cat([order, order[: self.total_size - n]])          # pad with the head
         assert len(order) == self.total_size
         mine = order[self.rank: self.total_size: self.num_replicas].contiguous()

@@ -296,8 +296,10 @@ class Solver:
         if distributed and not run_opts.optim.gradientClip:
             from .symm import try_make_allocator
             symm_alloc = try_make_allocator(device, args.world_size)
+        from .arena_linear import head_layout_groups
         arena = ParamArena(model.parameters(), criterion.parameters(), device=device,
-                           precision=args.precision, shared_allocator=symm_alloc)
+                           precision=args.precision, shared_allocator=symm_alloc,
+                           adjacent=head_layout_groups(model))
         if args.precision == Precision.BF16 and not _norm_accepts_fp32_stats(device):
             # BatchNorm running statistics stay fp32 (what the reference's checkpoints hold: a
             # bf16 EMA with momentum 0.1 stalls on small deltas); only if this torch build

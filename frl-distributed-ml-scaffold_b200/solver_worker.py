@@ -395,15 +395,13 @@ class SamplerState:
         return out
 
     def _pick(self, idx: torch.Tensor, data_batches, starts, target, output, meta, sample_metric):
+        """Rows ``idx`` (window-relative, device) of everything a ``SingleSample`` shows; metrics
+        and meta are looked up by global position from the per-split columns at the end."""
         n_fields = len(data_batches[0])
         return {"pos": idx + self._cur_samples,
                 "data": [self._gather_rows([d[f] for d in data_batches], starts, idx) for f in range(n_fields)],
                 "target": [tuple(t.index_select(0, idx) for t in head) for head in target],
-                "output": [o.index_select(0, idx) for o in output],
-                "metric": {k: v.reshape(len(v), -1)[:, 0].index_select(0, idx) if v.dim() > 1
-                           else v.index_select(0, idx) for k, v in sample_metric.items()},
-                "meta": {k: v.index_select(0, idx) for k, v in meta._asdict().items()
-                         if torch.is_tensor(v) and v.is_cuda}}
+                "output": [o.index_select(0, idx) for o in output]}
 
     @staticmethod
     def _cat_picks(a, b):
@@ -411,18 +409,14 @@ class SamplerState:
                 "data": [torch.cat([x, y]) for x, y in zip(a["data"], b["data"])],
                 "target": [tuple(torch.cat([x, y]) for x, y in zip(ha, hb))
                            for ha, hb in zip(a["target"], b["target"])],
-                "output": [torch.cat([x, y]) for x, y in zip(a["output"], b["output"])],
-                "metric": {k: torch.cat([a["metric"][k], b["metric"][k]]) for k in a["metric"]},
-                "meta": {k: torch.cat([a["meta"][k], b["meta"][k]]) for k in a["meta"]}}
+                "output": [torch.cat([x, y]) for x, y in zip(a["output"], b["output"])]}
 
     @staticmethod
     def _take(p, sel):
         return {"pos": p["pos"].index_select(0, sel),
                 "data": [x.index_select(0, sel) for x in p["data"]],
                 "target": [tuple(x.index_select(0, sel) for x in head) for head in p["target"]],
-                "output": [x.index_select(0, sel) for x in p["output"]],
-                "metric": {k: v.index_select(0, sel) for k, v in p["metric"].items()},
-                "meta": {k: v.index_select(0, sel) for k, v in p["meta"].items()}}
+                "output": [x.index_select(0, sel) for x in p["output"]]}
 
     def _fold_device(self, meta, data_batches, starts, n_group, target, output, sample_metric) -> None:
         base, dev = self._cur_samples, self._device
@@ -470,38 +464,59 @@ class SamplerState:
             self._dev_worst["score"] = keep_scores
 
     def _finish_device(self) -> None:
-        """The split's single device-to-host read: metric columns, the picks, the worst-k set."""
+        """The split's single device-to-host read: metric columns, the picks, the worst-k set —
+        every copy issued asynchronously into pinned memory, ONE stream synchronisation."""
+        pending: List[Tuple[torch.Tensor, torch.Tensor]] = []
+
+        def host(t: torch.Tensor) -> torch.Tensor:
+            if t.dtype == torch.bfloat16:
+                t = t.float()
+            dst = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            dst.copy_(t, non_blocking=True)
+            pending.append((dst, t))                  # keep the source alive until the sync
+            return dst
+
+        def host_pick(p):
+            return {"pos": host(p["pos"]), "data": [host(x) for x in p["data"]],
+                    "target": [tuple(host(x) for x in head) for head in p["target"]],
+                    "output": [host(x) for x in p["output"]],
+                    "score": host(p["score"]) if "score" in p else None}
+
+        n = self._cur_samples
+        cols_h = {k: host(v[:n]) for k, v in self._dev_cols.items()}
+        meta_h = {k: host(v[:n]) for k, v in self._dev_meta.items()}
+        random_h = [host_pick(p) for p in self._dev_random]
+        worst_h = host_pick(self._dev_worst) if self._dev_worst is not None else None
         torch.cuda.current_stream(self._device).synchronize()
-        cols = {k: v[:self._cur_samples].cpu().numpy() for k, v in self._dev_cols.items()}
+        pending.clear()
+
+        cols = {k: v.numpy().copy() for k, v in cols_h.items()}
         for k, v in cols.items():
             self._data_metric[k] = [v]
-        dev_meta = {k: v[:self._cur_samples].cpu() for k, v in self._dev_meta.items()}
+        dev_meta = {k: v.clone() for k, v in meta_h.items()}
 
-        def samples_of(p, limit=None) -> List[SingleSample]:
-            pos = p["pos"].cpu().tolist()
-            data = [x.cpu() for x in p["data"]]
-            target = [tuple(x.cpu() for x in head) for head in p["target"]]
-            output = [x.float().cpu() for x in p["output"]]
+        def samples_of(p, keep=None) -> List[SingleSample]:
             out = []
-            for r, g in enumerate(pos):
-                if limit is not None and not limit[r]:
+            for r, g in enumerate(p["pos"].tolist()):
+                if keep is not None and not keep[r]:
                     continue
                 meta = {k: v[g] for k, v in dev_meta.items()}
                 meta.update({k: v[g] for k, v in self._host_meta.items()})
-                out.append(SingleSample(data=[x[r] for x in data], target=[tuple(x[r] for x in h) for h in target],
-                                        meta=meta, output=[x[r] for x in output],
+                out.append(SingleSample(data=[x[r].clone() for x in p["data"]],
+                                        target=[tuple(x[r].clone() for x in h) for h in p["target"]],
+                                        meta=meta, output=[x[r].clone() for x in p["output"]],
                                         metric={k: cols[k][g] for k in cols}))
             return out
 
-        for p in self._dev_random:
+        for p in random_h:
             self._random_samples.extend(samples_of(p))
-        if self._dev_worst is not None:
-            finite = torch.isfinite(self._dev_worst["score"]).cpu().tolist()      # -inf = filtered out
-            scores = self._dev_worst["score"].cpu().tolist()
-            kept = samples_of(self._dev_worst, finite)
+        if worst_h is not None:
+            scores = worst_h["score"].tolist()
+            finite = [s != float("-inf") for s in scores]          # -inf = filtered out (invalid metric)
+            kept = samples_of(worst_h, finite)
             kept_scores = [s for s, f in zip(scores, finite) if f]
-            # heap order of the host path is unspecified beyond "the k most extreme": sort
-            # ascending by score like a drained min-heap would come out
+            # heap order of the host path is unspecified beyond "the k most extreme": ascending by
+            # score, as a drained min-heap would come out
             order = sorted(range(len(kept)), key=lambda i: kept_scores[i])
             self._worst_samples = [(kept_scores[i], kept[i]) for i in order]
         self._dev_random, self._dev_worst = [], None

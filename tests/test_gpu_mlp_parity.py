@@ -103,11 +103,12 @@ def _b200(algo, precision, graph, monkeypatch):
         if first_grads is None:
             torch.cuda.synchronize()
             first_grads = [worker.arena.grad_view(s).float().cpu().clone()
-                           for s in worker.arena.slots if s.is_model]
+                           for s in sorted(worker.arena.slots, key=lambda s: s.index) if s.is_model]
     torch.cuda.synchronize()
     if graph == "1":
         assert worker.graphed is not None and len(worker.graphed._graphs) == 1   # steps 4.. replayed
-    final = [worker.arena.master_view(s).cpu().clone() for s in worker.arena.slots if s.is_model]
+    final = [worker.arena.master_view(s).cpu().clone()
+             for s in sorted(worker.arena.slots, key=lambda s: s.index) if s.is_model]
     return np.asarray(rows, dtype=np.float64), first_grads, final
 
 
@@ -134,12 +135,13 @@ def _stock_gpu_first_grads():
 
 
 def _err(g, w):
+    """(median, 99.9th percentile, max) entry error relative to the tensor's peak, relative L2."""
     scale = float(w.abs().max())
     d = (g - w).abs()
     flat = d.flatten()[: 1 << 24].float()
     med = float(flat.median())
     q = float(torch.quantile(flat, 0.999)) if flat.numel() > 1000 else float(flat.max())
-    return med / scale, q / scale, float(d.max()) / scale
+    return med / scale, q / scale, float(d.max()) / scale, float((g - w).norm() / w.norm())
 
 
 @pytest.mark.parametrize("graph", ["0", "1"])
@@ -154,20 +156,24 @@ def test_mlp_config_matches_oracle_fp32(algo, graph, monkeypatch):
     # the ResNet tests document the same).
     np.testing.assert_allclose(rows[:1], want_rows[:1], rtol=1e-5, atol=0)
     np.testing.assert_allclose(rows[1:], want_rows[1:], rtol=1e-5 if algo == "sgd" else 1e-3, atol=0)
-    # first-step gradients.  (a) against stock fp32 torch on the SAME GPU: every entry within 1e-5
+    # first-step gradients.  (a) against stock fp32 torch on the SAME GPU: EVERY entry within 1e-5
     # of the tensor's peak — same contraction library, so this isolates this repo's kernels.
-    # (b) against the CPU oracle: the typical entry (median) within 1e-5 of the peak; single
-    # samples may differ by a ReLU unit at the rounding boundary (module docstring), which shows as
-    # a rank-one term on that sample's active rows, bounded here at 5 % of the peak.
+    # (b) against the CPU oracle: the typical entry (median) within 1e-5 of the peak and the whole
+    # tensor within 5e-2 in relative L2.  Entry-wise 1e-5 cannot hold across two devices for a ReLU
+    # net: measured with this seed, ONE unit of trunk layer 2 is on the other side of 0 for one
+    # sample on the CPU (module docstring) — its row of dW2 is off by 18 % of the peak, its db2
+    # entry by 6 %, everything upstream of it (dW1: 3.7e-3 on that sample's active rows) follows,
+    # layer 3 and both heads agree to 1e-6 — and stock torch on the GPU shows the identical picture.
     report = []
     for g, ws, wc in zip(grads, _stock_gpu_first_grads(), want_grads):
         report.append((tuple(wc.shape), _err(g, ws), _err(g, wc)))
-    print("fp32 first-step gradients (median, p99.9, max error / peak) vs stock torch on the GPU | vs CPU oracle:")
+    print("fp32 first-step gradients: (median, p99.9, max) entry error / peak, relative L2  "
+          "vs stock torch on the GPU | vs the CPU oracle")
     for shape, a, b in report:
-        print("  %-14s %.1e %.1e %.1e | %.1e %.1e %.1e" % ((str(shape),) + a + b))
+        print("  %-14s %.1e %.1e %.1e %.1e | %.1e %.1e %.1e %.1e" % ((str(shape),) + a + b))
     for shape, a, b in report:
         assert a[2] <= 1e-5, ("vs stock torch on the same GPU", shape, a)
-        assert b[0] <= 1e-5 and b[2] <= 5e-2, ("vs the CPU oracle", shape, b)
+        assert b[0] <= 1e-5 and b[3] <= 5e-2, ("vs the CPU oracle", shape, b)
     # six steps of weights vs the CPU oracle: SGD moves by lr*g; Adam turns last-bit gradient
     # differences into visible fractions of lr where v is tiny (final weights are
     # outside the 1e-5 claim)

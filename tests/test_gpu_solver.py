@@ -107,7 +107,9 @@ def test_first_step_gradients_match_reference(ns, golden_dir):
     worker.model.train()
     worker._pass_one_minibatch(0, ns.Split.TRAIN, data, target)
     torch.cuda.synchronize()
-    for i, s in enumerate(s for s in worker.arena.slots if s.is_model):
+    # parameter order (ArenaSlot.index), not arena order: the task heads' weights are laid out
+    # back to back (ParamArena(adjacent=...)) so the heads can run as one backward unit
+    for i, s in enumerate(sorted((s for s in worker.arena.slots if s.is_model), key=lambda s: s.index)):
         got = worker.arena.grad_view(s).cpu().numpy()
         np.testing.assert_allclose(got, g["grad_%02d" % i], rtol=1e-5, atol=1e-7)
 

@@ -2,6 +2,13 @@
 # 2 GPUs: multi-rank parity vs the CPU oracle (world 2), bench N=2 (parity_check inside), K7 launch-shape
 # sweep at world 2, stock-PyTorch arm N=2
 mkdir -p gpurun_out
+timeout 500 python -m pytest tests -m gpu -q --tb=short -s > gpurun_out/r2e_pytest.log 2>&1
+grep -E "passed|failed" gpurun_out/r2e_pytest.log | tail -2
+timeout 100 python tools/kernel_bench.py --only k4,k6 > gpurun_out/r2e_kernel_bench.log 2>&1
+cut -c1-150 gpurun_out/r2e_kernel_bench.log
+FRL_B200_EPOCH_TRACE=1 timeout 200 python bench.py --steps 20 --warmup 5 --profile gpurun_out/r2e_profile_mlp_b200.json > gpurun_out/r2e_bench_n1.json 2> gpurun_out/r2e_bench_n1.err
+python -c "import json; d=json.load(open('gpurun_out/r2e_bench_n1.json')); print('N=1: ms/step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'torch', d['torch_gpu_baseline']['ms_per_step'], 'roof', d['roofline']['frac'])"
+grep -E "epoch trace|loader trace" gpurun_out/r2e_bench_n1.err | tail -5 | cut -c1-300
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 timeout 300 $TR --master-port 29601 tests/run_ddp_vs_oracle.py > gpurun_out/r2e_ddp_parity_w2.log 2>&1
 echo "ddp parity world 2: $(grep -c DDP_PARITY_OK gpurun_out/r2e_ddp_parity_w2.log) rows ok"
