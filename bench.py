@@ -384,7 +384,7 @@ def run_torch_gpu(args, rank, local_rank, world, steps, warmup, with_e2e=True, p
             torch.cuda.synchronize()
         if rank == 0:
             rows = sorted(((e.key, e.device_time_total / 5.0, e.count / 5.0) for e in prof.key_averages()
-                           if e.device_time_total > 0), key=lambda r: -r[1])
+                           if e.device_time_total > 0 and str(getattr(e, "device_type", "")).endswith("CUDA")), key=lambda r: -r[1])
             with open(profile_path, "w") as f:
                 json.dump({"impl": "torch-gpu", "ms_per_step": ms, "kernels_us_per_step":
                            [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:40]]},
@@ -440,7 +440,7 @@ def main_torch_gpu(args, rank, local_rank, world):
                            "grad_allreduce": res["grad_sync"], "precision": res["precision"],
                            "step_issue": res["step"]},
                 "e2e": res.get("e2e"), "gpu_launches": 0, "clocks": clocks.summary()}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
@@ -743,7 +743,7 @@ def main_b200(args, rank, local_rank, world):
             torch.cuda.synchronize()
         if rank == 0:
             rows = sorted(((e.key, e.device_time_total / 5.0, e.count / 5.0) for e in prof.key_averages()
-                           if e.device_time_total > 0), key=lambda r: -r[1])
+                           if e.device_time_total > 0 and str(getattr(e, "device_type", "")).endswith("CUDA")), key=lambda r: -r[1])
             with open(args.profile, "w") as f:
                 json.dump({"impl": "b200", "ms_per_step": total_ms / K, "kernels_us_per_step":
                            [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:40]]},
@@ -816,7 +816,7 @@ def main_b200(args, rank, local_rank, world):
                 worker._pass_one_epoch(host_problem, loaders, Mode.TRAIN)
                 torch.cuda.synchronize()
             rows = sorted(((e.key, e.device_time_total / L, e.count / L) for e in prof.key_averages()
-                           if e.device_time_total > 0), key=lambda r: -r[1])
+                           if e.device_time_total > 0 and str(getattr(e, "device_type", "")).endswith("CUDA")), key=lambda r: -r[1])
             with open(args.profile.replace(".json", "") + "_e2e.json", "w") as f:
                 json.dump({"impl": "b200 e2e epoch", "steps": L, "kernels_us_per_step":
                            [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:40]]},
@@ -902,7 +902,7 @@ def main_b200(args, rank, local_rank, world):
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
                 "torch_gpu_baseline": torch_base, "parity_check": parity,
                 "clocks": clocks.summary(), "final_loss": float(losses[-1])}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         # Release the captured graphs (they hold NCCL work) before anything NCCL is torn down,
         # line the ranks up, and leave without running communicator destructors: a rank that
@@ -918,11 +918,40 @@ def main_b200(args, rank, local_rank, world):
         os._exit(0)
 
 
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its
+    version banner on stdout when the box exports NCCL_DEBUG), so file descriptor 1 is pointed at
+    stderr for the whole run and the line is written to the saved descriptor at the end."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str) -> None:
+        sys.stdout.flush()
+        os.write(saved, (line + "\n").encode())
+
+    return emit
+
+
+EMIT = None
+
+
+def emit_line(obj) -> None:
+    text = json.dumps(obj)
+    if EMIT is not None:
+        EMIT(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
+    global EMIT
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl != "reference":
+        EMIT = claim_stdout()
     if args.impl == "reference":
         main_reference(args, rank)
         return

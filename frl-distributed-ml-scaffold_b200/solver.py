@@ -300,7 +300,8 @@ class Solver:
         arena = ParamArena(model.parameters(), criterion.parameters(), device=device,
                            precision=args.precision, shared_allocator=symm_alloc,
                            adjacent=head_layout_groups(model))
-        if args.precision == Precision.BF16 and not _norm_accepts_fp32_stats(device):
+        if (args.precision == Precision.BF16 and any(b.is_floating_point() for b in model.buffers())
+                and not _norm_accepts_fp32_stats(device)):
             # BatchNorm running statistics stay fp32 (what the reference's checkpoints hold: a
             # bf16 EMA with momentum 0.1 stalls on small deltas); only if this torch build
             # refuses bf16 activations/affine parameters next to fp32 statistics are the buffers

