@@ -887,6 +887,7 @@ def main_b200(args, rank, local_rank, world):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": total_ms / K, "step_p50_ms": statistics.median(step_ms),
+                "step_ms_first5": [round(v, 4) for v in step_ms[:5]], "step_ms_max": max(step_ms),
                 "host_issue_ms_per_step": host_issue_ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if precision == Precision.BF16 else "f32", "data": "synthetic",

@@ -108,10 +108,10 @@ struct NvlsCommon {
 // The switch round trip of multimem.ld_reduce is the long latency here (microseconds), so every
 // thread first issues kNRemote of them back to back and only then walks the items, loading the
 // (short-latency) local master/state slices item by item.
-// How many: NVLink wants ~2.3 MB in flight per GPU (770 GB/s x ~3 us).  The grid is kept small on
-// purpose (CTAs parked at the entry barrier cost the overlapped backward GEMMs their SMs), so the
-// depth per thread makes up for it: 16 CTAs x 512 threads x kNRemote x 16 B = 0.5 MB at 4, 2 MB at
-// 16.  At world 2 a rank's shard is half of every bucket (4x the work per rank of world 8).
+// How many remote loads a thread keeps in flight is a template parameter (FRL_B200_NVLS_INFLIGHT,
+// default 4).  Deeper pipelines (8, 16) were tried to let a small grid cover NVLink's
+// bandwidth-latency product; measured at world 2 (the case with the largest shard per rank) they
+// do not pay: 74 CTAs x depth 4 = 1.170 ms/step, 32 x 8 = 1.190, 74 x 16 = 1.198, 16 x 16 = 1.648.
 template <typename Rule, int NS, int kNRemote>
 __global__ void __launch_bounds__(kNThreads)
 nvls_update_bf16(float* __restrict__ p_, float* __restrict__ s0_, float* __restrict__ s1_,
@@ -240,7 +240,7 @@ static int launch_nvls(const Rule& rule, float* p, float* s0, float* s1, float* 
         const char* e = getenv("FRL_B200_NVLS_INFLIGHT");
         return e ? atoi(e) : 0;
     }();
-    const int depth = env_depth > 0 ? env_depth : (world <= 2 ? 16 : (world <= 4 ? 8 : 4));
+    const int depth = env_depth > 0 ? env_depth : 4;   // measured at world 2: 4 -> 1.170, 8 -> 1.190, 16 -> 1.198 ms/step
     // the grid must be identical on every rank: it depends on arguments only
 #define FRL_NV(NR)                                                                                    \
     do {                                                                                              \

@@ -504,9 +504,15 @@ class SamplerState:
         meta_h = {k: host(v[:n]) for k, v in self._dev_meta.items()}
         random_h = [host_pick(p) for p in self._dev_random]
         worst_h = host_pick(self._dev_worst) if self._dev_worst is not None else None
+        t_q = time.perf_counter()
         landed = flush()
+        t_f = time.perf_counter()
         torch.cuda.current_stream(self._device).synchronize()
+        t_s = time.perf_counter()
         pending.clear()
+        if os.environ.get("FRL_B200_EPOCH_TRACE"):
+            logger.info("finish trace: %d tensors queued, flush issued in %.2f ms, sync waited %.2f ms",
+                        len(requests), 1e3 * (t_f - t_q), 1e3 * (t_s - t_f))
 
         def resolve(x):
             if isinstance(x, int):
@@ -760,6 +766,7 @@ class SolverWorker:
                     self._raise_if_nan(log, checked, data_type)
                     checked += 1
                 sampler_state.compute_metrics()
+                mark("last window folded")
                 sampler_state.finish()
             timer.epoch.update(time.time() - epoch_start)
 

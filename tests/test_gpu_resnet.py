@@ -158,8 +158,11 @@ def test_resnet_configs_match_stock_torch_on_the_same_gpu(ns, case, monkeypatch)
         want_delta = (v.cpu() - initial[k]).double().numpy().ravel()
         got_delta = (final["state_dict"][k].double() - initial[k].double()).numpy().ravel()
         rel = np.linalg.norm(got_delta - want_delta) / np.linalg.norm(want_delta)
-        # measured: SGD <= 0.5 %, Adam up to 3.3 % at conv1 (sign-like steps where |g| ~ rounding)
-        assert rel <= (0.10 if CASES[case][1] == "adam" else 0.02), (k, rel)
+        # measured: SGD <= 0.5 %; Adam up to 3.3 % at conv1 with per-head backward GEMMs and up to
+        # 11.7 % at a BatchNorm weight once the four heads run as one backward unit (their dX is
+        # summed in another order; Adam's sign-like steps turn that into whole-lr differences
+        # wherever |g| ~ rounding)
+        assert rel <= (0.15 if CASES[case][1] == "adam" else 0.02), (k, rel)
 
 
 def test_resnet18_bf16_mode_tracks_the_oracle(ns):
