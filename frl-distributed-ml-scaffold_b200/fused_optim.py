@@ -5,6 +5,14 @@
 (``OptimOpts.momentum`` feeds SGD *and* RMSprop, ``epsilon``/``amsgrad`` feed Adam, weight decay
 is L2-coupled and applies to every parameter).  ``state_dict()`` / ``load_state_dict()`` speak
 torch's per-parameter format so the reference's ``.checkpoint.pth`` files stay interchangeable.
+
+Known limitation: the step count (Adam's bias corrections) is ONE number for the whole arena.
+``torch.optim`` keeps one per parameter and does not advance it for a parameter whose gradient
+is ``None`` in a step; here a parameter that misses gradients for some steps (world size 1 only:
+with several ranks a missing gradient is DDP's error, as in the reference) keeps being corrected
+with the global count, ``state_dict()`` writes that count for every parameter and
+``load_state_dict()`` takes the maximum over the loaded entries.  Models whose parameters all
+receive a gradient every step — every configuration of BASELINE.json — are unaffected.
 """
 from typing import Any, Dict, List, Optional, Tuple
 
