@@ -436,3 +436,110 @@ def test_reused_and_tied_linears_wait_for_their_last_gradient(tmp_path, patched)
         ref_opt.step()
     for a, b in zip(r0, ref.parameters()):
         np.testing.assert_allclose(a.numpy(), b.detach().numpy(), rtol=2e-5, atol=2e-7)
+
+
+# ---- round-2 host logic: arena layout groups, bucket merging, quiet randperm, multi-head unit ------
+
+def test_adjacent_groups_keep_parameter_positions_and_sorted_offsets():
+    torch.manual_seed(0)
+    trunk = nn.Linear(16, 24)
+    heads = [nn.Linear(24, 8), nn.Linear(24, 16), nn.Linear(24, 5)]
+    params = list(trunk.parameters()) + [p for h in heads for p in h.parameters()]
+    groups = [[h.weight for h in heads], [h.bias for h in heads]]
+    arena = ParamArena(params, device="cpu", adjacent=groups)
+    assert len(arena.adjacent_groups) == 2
+    offs = [s.offset for s in arena.slots]
+    assert offs == sorted(offs)                                  # slot list stays in layout order
+    by_param = {id(s.param): s for s in arena.slots}
+    for s in arena.slots:                                        # optimizer position = parameter order
+        assert params[s.index] is s.param
+    w = [by_param[id(h.weight)] for h in heads]
+    assert w[0].end == w[1].offset and w[1].end == w[2].offset   # back to back, no padding
+    b = [by_param[id(h.bias)] for h in heads]
+    assert b[0].end == b[1].offset and b[1].end == b[2].offset
+    for p, before in zip(params, [p.detach().clone() for p in params]):
+        assert torch.equal(p, before)
+    # a group whose inner members are not multiples of 8 elements is ignored, not half-applied
+    odd = [nn.Linear(3, 5), nn.Linear(3, 7)]
+    plain = ParamArena([p for m in odd for p in m.parameters()], device="cpu",
+                       adjacent=[[m.weight for m in odd]])
+    assert plain.adjacent_groups == [] and [s.index for s in plain.slots] == [0, 1, 2, 3]
+
+
+def test_lone_bias_bucket_absorbs_its_weight():
+    """6 -> 4 buckets on the MLP layout: a tiny open bucket takes the next oversize tensor in."""
+    layers = []
+    for _ in range(3):
+        layers += [nn.Linear(4096, 4096), nn.ReLU()]
+    net = nn.Sequential(*layers, nn.Linear(4096, 1000))
+    arena = ParamArena(net.parameters(), device="cpu", precision=Precision.BF16)
+    buckets = arena.buckets(24 << 20)
+    assert len(buckets) == 4
+    assert buckets[0][1] == arena.numel and buckets[-1][0] == 0
+    assert all(a[0] == b[1] for a, b in zip(buckets[:-1], buckets[1:]))
+    slot_of = {s.offset: s for s in arena.slots}
+    for lo, hi in buckets:                                       # whole tensors only
+        assert lo in slot_of and any(s.end == hi or arena.numel == hi for s in arena.slots)
+
+
+def test_quiet_randperm_is_torch_randperm():
+    from frl_b200.device_loader import randperm_quiet
+    for n in (1, 7, 1000, 100_000):
+        g1, g2 = torch.Generator().manual_seed(n), torch.Generator().manual_seed(n)
+        threads = torch.get_num_threads()
+        assert torch.equal(torch.randperm(n, generator=g1), randperm_quiet(n, g2))
+        assert torch.equal(g1.get_state(), g2.get_state()) and torch.get_num_threads() == threads
+
+
+def test_multihead_unit_matches_per_head_autograd(double):
+    """The task heads as one backward unit (one dX / one dW over adjacent arena weights) against
+    stock autograd + torch SGD, three heads with a bias size that is not a multiple of 8."""
+    from frl_b200 import arena_linear
+    from frl_b200.model import ListSelect, MultiTaskModel
+    arena_linear.KERNELS, saved = double, arena_linear.KERNELS
+    try:
+        def build():
+            torch.manual_seed(1)
+            trunk = nn.Sequential(ListSelect(sel_index=0, num_elements=1), nn.Linear(16, 24), nn.ReLU())
+            return MultiTaskModel(trunk, [nn.Linear(24, 8), nn.Linear(24, 16), nn.Linear(24, 5)])
+        net, ref = build(), build()
+        arena = ParamArena(net.parameters(), device="cpu", adjacent=arena_linear.head_layout_groups(net))
+        opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm.SGD, lr=0.05))
+        pipe = grad_sync.GradBucketPipeline(arena, opt, world_size=1, eager_update=False)
+        assert pipe.patch_linears(net) == 4
+        assert sum(s.multihead is not None for s in pipe.linear_sites) == 1 and "forward" in net.__dict__
+        ref_opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-5)
+        net.train(), ref.train()
+        g = torch.Generator().manual_seed(3)
+        for _ in range(3):
+            x = torch.randn(12, 16, generator=g)
+            outs = net([x])
+            pipe.begin_step()
+            sum(o.square().mean() for o in outs).backward()
+            pipe.finish_step()
+            ref_opt.zero_grad()
+            sum(o.square().mean() for o in ref([x])).backward()
+            ref_opt.step()
+        for a, b in zip(net.parameters(), ref.parameters()):
+            np.testing.assert_allclose(a.detach().numpy(), b.detach().numpy(), rtol=1e-5, atol=1e-7)
+        pipe.unpatch_linears()
+        assert "forward" not in net.__dict__                        # pickles as a plain module
+        with torch.no_grad():
+            assert len(net([torch.randn(2, 16)])) == 3
+    finally:
+        arena_linear.KERNELS = saved
+
+
+def test_metric_hooks_run_synchronously_unless_the_problem_opts_in(monkeypatch):
+    """Round-1 ADVICE (medium): host-returning metric hooks are folded on the training thread,
+    as the reference does; the worker thread is opt-in."""
+    import frl_b200.solver_worker as sw
+    from frl_b200.problem import Ordering
+
+    class P:
+        def get_rankable_metric(self):
+            return "m", Ordering.DESC
+
+    monkeypatch.delenv("FRL_B200_ASYNC_METRICS", raising=False)
+    s = sw.SamplerState(P(), 10, 10, torch.device("cpu"), 2)
+    assert s._runner is None
