@@ -759,14 +759,22 @@ class SolverWorker:
                     batch_start = time.time()
 
                 mark("last step issued")
+                # the last window's fold is queued BEHIND the last steps (device-returning hooks:
+                # pure device work, no host read) so the stream drains once, not twice; a NaN in
+                # the last steps is still raised first — the fold's results are simply dropped
+                # with the exception
+                fold_early = bool(sampler_state._dev_mode)
+                if fold_early:
+                    sampler_state.compute_metrics()
+                    mark("last window folded")
                 if self.device.type == "cuda":
                     torch.cuda.current_stream().synchronize()
                 mark("stream drained")
                 while checked < n_batches:
                     self._raise_if_nan(log, checked, data_type)
                     checked += 1
-                sampler_state.compute_metrics()
-                mark("last window folded")
+                if not fold_early:           # host-returning hooks: after the NaN guard, as before
+                    sampler_state.compute_metrics()
                 sampler_state.finish()
             timer.epoch.update(time.time() - epoch_start)
 
