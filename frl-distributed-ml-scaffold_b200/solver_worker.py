@@ -440,7 +440,9 @@ class SamplerState:
             return
         picks = sorted(j - base for j in self._random_indices if base <= j < base + n_group)
         if picks:
-            idx = torch.tensor(picks, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+            # a few int64s from pageable memory: the driver stages them, the host does not wait
+            # for the device (a pinned allocation here would cost a ~0.5 ms system call)
+            idx = torch.tensor(picks, dtype=torch.int64, device=dev)
             self._dev_random.append(self._pick(idx, data_batches, starts, target, output, meta, sample_metric))
         # worst-k of this window, merged into the running set: all on the device
         scores = sample_metric[self._rankable_metric].reshape(n_group).float()
