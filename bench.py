@@ -783,6 +783,16 @@ def main_b200(args, rank, local_rank, world):
         out_dtype = torch.bfloat16 if precision == Precision.BF16 else torch.float32
         if world > 1:
             tolerant = getattr(host_ds.device_transform, "bf16_wire_fields", ()) if out_dtype == torch.bfloat16 else ()
+            # the global dataset lives in /dev/shm: shorten the epoch if the box's tmpfs is small
+            row_bytes = sum(t[0].numel() * (2 if (k in tolerant and t.dtype == torch.float32) else t.element_size())
+                            for k, t in host_ds.pinned_fields.items())
+            st = os.statvfs("/dev/shm")
+            fit = int(0.7 * st.f_bavail * st.f_frsize // max(row_bytes * B * world, 1))
+            if fit < L:
+                assert fit >= 4, "/dev/shm too small for a 4-step epoch of the global dataset"
+                log("note: /dev/shm holds only %d steps of the global dataset; epoch shortened from %d" % (fit, L))
+                L = fit
+                n_epochs_timed = max(1, K // L)
             host_ds.pinned_fields = shared_global_fields(host_ds.pinned_fields, L * B * world, rank, dev,
                                                          bf16_fields=tuple(tolerant))
             host_ds._n = L * B * world
