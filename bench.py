@@ -458,21 +458,45 @@ BYTES_PER_PARAM = {  # algorithmic, fp32 master + state, bf16 gradient read, bf1
     ("rmsprop", "bf16"): 2 + 4 * 3 + 4 * 3 + 2, ("rmsprop", "fp32"): 4 * 4 + 4 * 3}
 
 
-def shared_global_fields(sample_fields, n_rows, rank, dev, bf16_fields=()):
-    """world > 1: one copy of the synthetic dataset for the whole box.  Rank 0 writes every field
-    as a file in /dev/shm (a base block of random rows tiled to ``n_rows``: the values are
-    synthetic, the row count and byte volume are what the loop sees), every rank maps the files and
-    page-locks the mapping (cudaHostRegister) so its GPU can read the rows in place."""
+def gpu_numa_node(local_rank):
+    """NUMA node the GPU hangs off (sysfs, via its PCI bus id); 0 if unknown."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus.lower()[-12:]) as f:
+            return max(int(f.read().strip()), 0)
+    except Exception:                                   # noqa: BLE001
+        return 0
+
+
+def shared_global_fields(sample_fields, n_rows, rank, local_rank, world, dev, bf16_fields=()):
+    """world > 1: ONE copy of the synthetic dataset per NUMA node of the box.  The lowest rank of
+    each node (its threads are bound to the node: first touch lands there) writes every field as
+    a file in /dev/shm (a base block of random rows tiled to ``n_rows``, same generator seed on
+    every node: the copies are identical; the values are synthetic, the row count and byte volume
+    are what the loop sees); every rank maps its node's files and page-locks the mapping
+    (cudaHostRegister) so its GPU reads the rows in place over its own PCIe link without crossing
+    the socket interconnect."""
     import torch
     import torch.distributed as dist
     tag = os.environ.get("MASTER_PORT", "0")
+    node = gpu_numa_node(local_rank)
+    nodes = [None] * world
+    dist.all_gather_object(nodes, node)
+    writer = min(r for r in range(world) if nodes[r] == node) == rank
     out = {}
-    paths = {name: "/dev/shm/frl_b200_bench_%s_%s.bin" % (tag, name) for name in sample_fields}
+    paths = {name: "/dev/shm/frl_b200_bench_%s_n%d_%s.bin" % (tag, node, name) for name in sample_fields}
     # fields the transform declares bf16-tolerant are stored in that wire dtype (what the loader
     # would otherwise make of them once per rank: world copies of the global array)
     sample_fields = {k: (v.to(torch.bfloat16) if k in bf16_fields and v.dtype == torch.float32 else v)
                      for k, v in sample_fields.items()}
-    if rank == 0:
+    if writer:
+        try:
+            torch.set_num_threads(max(1, min(16, len(os.sched_getaffinity(0)))))
+        except AttributeError:
+            pass
         g = torch.Generator().manual_seed(7)
         for name, sample in sample_fields.items():
             shape = (n_rows,) + tuple(sample.shape[1:])
@@ -500,10 +524,10 @@ def shared_global_fields(sample_fields, n_rows, rank, dev, bf16_fields=()):
         assert t.is_pinned()
         out[name] = t
     dist.barrier()
-    if rank == 0:
+    if writer:
         for path in paths.values():
             os.unlink(path)                   # the mappings keep the memory alive
-    return out
+    return out, len(set(nodes))
 
 
 def nvls_parity_check(worker, step_fn, world, algo, precision):
@@ -787,14 +811,14 @@ def main_b200(args, rank, local_rank, world):
             row_bytes = sum(t[0].numel() * (2 if (k in tolerant and t.dtype == torch.float32) else t.element_size())
                             for k, t in host_ds.pinned_fields.items())
             st = os.statvfs("/dev/shm")
-            fit = int(0.7 * st.f_bavail * st.f_frsize // max(row_bytes * B * world, 1))
+            fit = int(0.7 * st.f_bavail * st.f_frsize // max(2 * row_bytes * B * world, 1))   # a copy per NUMA node
             if fit < L:
                 assert fit >= 4, "/dev/shm too small for a 4-step epoch of the global dataset"
                 log("note: /dev/shm holds only %d steps of the global dataset; epoch shortened from %d" % (fit, L))
                 L = fit
                 n_epochs_timed = max(1, K // L)
-            host_ds.pinned_fields = shared_global_fields(host_ds.pinned_fields, L * B * world, rank, dev,
-                                                         bf16_fields=tuple(tolerant))
+            host_ds.pinned_fields, n_copies = shared_global_fields(
+                host_ds.pinned_fields, L * B * world, rank, local_rank, world, dev, bf16_fields=tuple(tolerant))
             host_ds._n = L * B * world
         sampler = None
         if world > 1:
@@ -841,7 +865,7 @@ def main_b200(args, rank, local_rank, world):
                "gpu_launches": e2e_launches,
                "epoch_losses": {k: float(v) for k, v in ep_losses.items()},
                "sampler": ("ScaffoldSampler (global randperm seeded by the epoch, padded, [rank::world]) over "
-                           "one global dataset of %d samples in shared pinned host memory" % (L * B * world))
+                           "one global dataset of %d samples in shared pinned host memory (a copy per NUMA node: %d)" % (L * B * world, n_copies))
                           if world > 1 else "RandomSampler (the reference's single-process loader)",
                "how": "SolverWorker._pass_one_epoch (the loop Solver.solve runs per epoch) over the "
                       "Problem's dataset (%d batches per rank) in pinned host memory, model inputs stored in "
