@@ -665,6 +665,16 @@ def main_b200(args, rank, local_rank, world):
         worker._pass_one_minibatch(i, t.Split.TRAIN, data, target)
 
     # ======================= leg 1: inputs resident in HBM =======================
+    # spin-up: a GPU that sat idle (every GPU but the first on a fresh multi-GPU box) needs tens of
+    # milliseconds of load to reach its clocks — longer than W warm-up steps of ~1 ms.  Not a
+    # training step: a plain GEMM loop on scratch tensors, before the warm-up steps.
+    spin = torch.randn(4096, 4096, device=dev, dtype=torch.bfloat16)
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.25:
+        for _ in range(20):
+            spin = (spin @ spin).clamp_(-1, 1)
+        torch.cuda.synchronize()
+    del spin
     for i in range(W):
         step_resident(i)
     barrier()
@@ -927,6 +937,7 @@ def main_b200(args, rank, local_rank, world):
                 "dtype": "bf16" if precision == Precision.BF16 else "f32", "data": "synthetic",
                 "config": {"workload": workload_name(args), "global_batch": B * world,
                            "step_issue": "CUDA graph replay" if args.graph else "eager",
+                           "spin_up": "0.25 s GEMM loop on scratch tensors before the warm-up steps (clock ramp of an idle GPU; not a training step)",
                            "parallelism": "dp%d" % world,
                            "precision": "bf16 forward/backward + bf16 grads, fp32 master weights and "
                                         "optimizer state" if precision == Precision.BF16 else "fp32",
