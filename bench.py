@@ -502,7 +502,8 @@ def shared_global_fields(sample_fields, n_rows, rank, local_rank, world, dev, bf
             shape = (n_rows,) + tuple(sample.shape[1:])
             t = torch.from_file(paths[name], shared=True, size=int(torch.tensor(shape).prod()),
                                 dtype=sample.dtype).view(shape)
-            base = min(n_rows, 32768)
+            row_bytes = max(int(sample[0].numel()) * sample.element_size(), 1)
+            base = max(1, min(n_rows, 32768, (1 << 29) // row_bytes))      # <= 512 MB of fresh random rows
             if sample.dtype in (torch.float32, torch.bfloat16):
                 t[:base].copy_(torch.randn((base,) + shape[1:], generator=g))
             elif sample.dtype == torch.uint8:
