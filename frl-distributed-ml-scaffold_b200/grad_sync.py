@@ -352,15 +352,16 @@ class GradBucketPipeline:
         self.optimizer.end_step()
 
     def _tail_update(self) -> None:
-        coef = None
         if self.clip_norm > 0.0:
-            # the global norm needs every gradient first: gather the stragglers, then K3 + K2
+            # the global norm needs every gradient first: gather the stragglers into the arena,
+            # then K3 + K2 over the arena (the clip coefficient applies to model parameters only)
             self._flatten_stragglers(self.arena.slots, "all", side=False)
             n_model = self.arena.model_end
             KERNELS.grad_sumsq_clip(self.arena.grad[:n_model], n_model, pre_scale=self.grad_scale,
                                     max_norm=self.clip_norm, out3=self.clip_out,
                                     scratch=self.clip_scratch)
-            coef = self.clip_out[2:3]
+            self._update(0, self.arena.numel, self.clip_out[2:3])
+            return
         if self._ext and not self.distributed:
             # one GPU: the update reads every gradient where it lies — no flatten pass
             table = self.tables.whole()
@@ -370,7 +371,7 @@ class GradBucketPipeline:
             if not self._keep_ext:
                 self._ext.clear()
             return
-        self._update(0, self.arena.numel, coef)
+        self._update(0, self.arena.numel, None)
 
     def _update_table(self, table) -> None:
         if self.record_update_events and self.on_cuda:

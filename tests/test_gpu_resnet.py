@@ -176,3 +176,78 @@ def test_resnet18_bf16_mode_tracks_the_oracle(ns):
     np.testing.assert_allclose(rows[1], want[1], rtol=3e-2, atol=3e-2)
     assert np.isfinite(rows).all()
     assert worker.arena.grad.dtype == torch.bfloat16
+
+
+@pytest.mark.parametrize("graph", ["0", "1"])
+@pytest.mark.parametrize("clip", [0.0, 0.5])
+def test_conv_gradients_read_in_place_with_and_without_clipping(ns, monkeypatch, graph, clip):
+    """A small convolutional 2-task Problem (no normalisation layers, so it is not chaotic): the
+    convolution gradients reach the update through the segment tables (K2-mt on one GPU; with
+    clipping: K1 flatten -> K3 -> K2), the two heads run as one backward unit, and from the fifth
+    step on the step is replayed from a CUDA graph whose tail runs outside it.  8 steps of SGD
+    against the stock-torch loop on the same GPU: losses 1e-4, final weights 1e-4 of their peak."""
+    import torch.nn as nn
+    monkeypatch.setenv("FRL_B200_CUDA_GRAPH", graph)
+    monkeypatch.setenv("FRL_B200_CUDNN_BENCHMARK", "0")
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.deterministic,
+           torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark, torch.backends.cudnn.deterministic = False, True
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+
+    def make(save_dir):
+        Reg, Cls = synthetic._task_classes(ns)
+        tasks = [Cls(32, 10, 1.0, field="y_cls", name="cls"), Reg(32, 4, 1.0, field="y_reg", name="reg")]
+        heads = [("cls", 10, "y_cls", "cls"), ("reg", 4, "y_reg", "reg")]
+
+        def base():
+            return nn.Sequential(ns.model.ListSelect(sel_index=0, num_elements=1),
+                                 nn.Conv2d(3, 16, 3, padding=1), nn.ReLU(), nn.Conv2d(16, 32, 3, stride=2, padding=1),
+                                 nn.ReLU(), nn.AdaptiveAvgPool2d(1), nn.Flatten())
+        fields = [(ns.Split.TRAIN, synthetic.resnet_fields(64, 16, heads, 0))]
+        return synthetic._problem_class(ns)(tasks, [], fields, save_dir, shift=0.0, scale=1.0, base_factory=base)
+
+    t = ns.types
+    run_opts = t.RunOpts(optim=t.OptimOpts(algo=t.OptAlgorithm.SGD, lr=0.05, gradientClip=clip), batchSize=8,
+                         nEpochs=1, numThreads=0, singleThreaded=True, numVisualizedSamples=0)
+    try:
+        # stock torch on the GPU
+        torch.manual_seed(SEED)
+        ref_problem = make("/tmp/unused")
+        ref_model = ref_problem.get_model()
+        crit = ref_problem.get_criterion()
+        spec = ref_loop.RunSpec(optim=ref_loop.OptimSpec(algo="sgd", lr=0.05, gradient_clip=clip), batch_size=8, n_epochs=1)
+        trace = ref_loop.train(ref_model, list(crit.loss_modules), list(crit.loss_weights), list(crit.loss_names),
+                               [(d.data_type.value, d) for d in ref_problem.datasets], spec,
+                               device=torch.device("cuda", 0))
+        # this repo
+        save_dir = tempfile.mkdtemp(prefix="frl_b200_conv_")
+        problem = make(save_dir)
+        captured = {}
+        orig = Solver.build_worker.__func__
+
+        def spy(cls, args):
+            worker, sched, ckpt = orig(cls, args)
+            captured["worker"] = worker
+            return worker, sched, ckpt
+
+        Solver.build_worker = classmethod(spy)
+        try:
+            torch.manual_seed(SEED)
+            list(Solver.solve(run_opts, problem, group_name=None, init_method="file:///tmp/unused"))
+        finally:
+            Solver.build_worker = classmethod(orig)
+    finally:
+        (torch.backends.cudnn.benchmark, torch.backends.cudnn.deterministic,
+         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32) = old
+    worker = captured["worker"]
+    assert worker.pipeline.mt_enabled and sum(s.multihead is not None for s in worker.pipeline.linear_sites) == 1
+    if graph == "1":
+        assert worker.graphed is not None and len(worker.graphed._graphs) == 1
+    rows = np.concatenate([r for _, _, r in worker.loss_history])
+    want = np.concatenate([trace.losses[k] for k in sorted(trace.losses)])
+    assert rows.shape == want.shape == (8, 3)
+    np.testing.assert_allclose(rows, want, rtol=1e-4, atol=1e-6)
+    final = torch.load(os.path.join(save_dir, "final_model.pth"), weights_only=False)["state_dict"]
+    for k, v in ref_model.state_dict().items():
+        peak = float(v.abs().max())
+        assert float((final[k] - v.cpu()).abs().max()) <= 1e-4 * peak, k
