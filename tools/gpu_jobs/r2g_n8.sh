@@ -2,11 +2,12 @@
 # 8 GPUs (one box): multi-rank parity vs the CPU oracle at world 4 and 8, bench N=8 / N=4 (parity_check inside),
 # stock-PyTorch arm N=8, ResNet workloads N=8
 mkdir -p gpurun_out
+LAST='import sys,json; d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith("{")][-1])'
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-timeout 300 $TR --nproc-per-node 4 --master-port 29701 tests/run_ddp_vs_oracle.py > gpurun_out/r2g_ddp_parity_w4.log 2>&1
-echo "ddp parity world 4: $(grep -c DDP_PARITY_OK gpurun_out/r2g_ddp_parity_w4.log) rows ok"
 timeout 300 $TR --nproc-per-node 8 --master-port 29702 tests/run_ddp_vs_oracle.py > gpurun_out/r2g_ddp_parity_w8.log 2>&1
 echo "ddp parity world 8: $(grep -c DDP_PARITY_OK gpurun_out/r2g_ddp_parity_w8.log) rows ok"
+timeout 300 $TR --nproc-per-node 4 --master-port 29701 tests/run_ddp_vs_oracle.py > gpurun_out/r2g_ddp_parity_w4.log 2>&1
+echo "ddp parity world 4: $(grep -c DDP_PARITY_OK gpurun_out/r2g_ddp_parity_w4.log) rows ok"
 timeout 400 $TR --nproc-per-node 8 --master-port 29703 bench.py --gpus 8 --steps 20 --warmup 5 \
     --profile gpurun_out/r2g_profile_mlp_b200_n8.json > gpurun_out/r2g_bench_n8.json 2> gpurun_out/r2g_bench_n8.err
 timeout 300 $TR --nproc-per-node 4 --master-port 29704 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r2g_bench_n4.json 2> gpurun_out/r2g_bench_n4.err
@@ -18,9 +19,11 @@ timeout 400 $TR --nproc-per-node 8 --master-port 29707 bench.py --gpus 8 --workl
     > gpurun_out/r2g_bench_r50_n8.json 2> gpurun_out/r2g_bench_r50_n8.err
 python - <<'PY'
 import json
+def load(p):
+    return json.loads([l for l in open(p).read().splitlines() if l.startswith("{")][-1])
 for name in ("bench_n8", "bench_n4", "torch_n8", "bench_r18_n8", "bench_r50_n8"):
     try:
-        d = json.load(open("gpurun_out/r2g_%s.json" % name))
+        d = load("gpurun_out/r2g_%s.json" % name)
         e = d.get("e2e") or {}
         print(name, "value %.0f ms/step %.3f" % (d["value"], d["ms_per_step"]), "e2e ms", e.get("ms_per_step"),
               "parity", (d.get("parity_check") or {}).get("ok"), "torch ms", (d.get("torch_gpu_baseline") or {}).get("ms_per_step"))
