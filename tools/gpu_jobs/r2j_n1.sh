@@ -15,6 +15,8 @@ python -c "$LAST; print('100 steps: resident', d['ms_per_step'], 'e2e', d['e2e']
 timeout 200 python bench.py --algo adam --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2j_bench_n1_adam.json 2> /dev/null
 python -c "$LAST; print('adam: resident', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'roof', d['roofline']['frac'], 'torch', d['torch_gpu_baseline']['ms_per_step'])" < gpurun_out/r2j_bench_n1_adam.json
 timeout 200 python bench.py --impl torch-gpu --steps 10 --warmup 5 --no-e2e --profile gpurun_out/r2j_profile_mlp_torch.json > gpurun_out/r2j_torch_n1.json 2> /dev/null
+timeout 200 python bench.py --impl torch-gpu --torch-optim fused --steps 20 --warmup 5 --no-e2e > gpurun_out/r2j_torch_n1_fused.json 2> /dev/null
+python -c "$LAST; print('torch-gpu fused optimizer: ms/step', d['ms_per_step'])" < gpurun_out/r2j_torch_n1_fused.json
 for wl in resnet18 resnet50x4; do
   timeout 300 python bench.py --workload $wl --steps 10 --warmup 5 --cpu-steps 1 > gpurun_out/r2j_bench_$wl.json 2> gpurun_out/r2j_bench_$wl.err
   python -c "$LAST; print('$wl: ms/step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'torch', d['torch_gpu_baseline']['ms_per_step'], 'roof', d['roofline']['frac'], d['roofline']['avg_launch_ms'])" < gpurun_out/r2j_bench_$wl.json
