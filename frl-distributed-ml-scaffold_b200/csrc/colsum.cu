@@ -172,7 +172,8 @@ static inline int colsum_splits(int64_t rows, int64_t tiles) {
         return v < 1 ? 1 : v;
     }();
     int64_t want = (static_cast<int64_t>(sm_count()) * ctas_per_sm + tiles - 1) / tiles;
-    const int64_t max_by_rows = (rows + kSWarps - 1) / kSWarps;
+    // at least 8 rows per warp: below that the per-tile fold of the splits outweighs the stream
+    const int64_t max_by_rows = (rows + kSWarps * 8 - 1) / (kSWarps * 8);
     if (want > max_by_rows) want = max_by_rows;
     if (want > kSMaxSplits) want = kSMaxSplits;
     if (want < 1) want = 1;
