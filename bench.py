@@ -384,10 +384,11 @@ def run_torch_gpu(args, rank, local_rank, world, steps, warmup, with_e2e=True, p
             torch.cuda.synchronize()
         if rank == 0:
             rows = sorted(((e.key, e.device_time_total / 5.0, e.count / 5.0) for e in prof.key_averages()
-                           if e.device_time_total > 0 and str(getattr(e, "device_type", "")).endswith("CUDA")), key=lambda r: -r[1])
+                           if e.device_time_total > 0 and str(getattr(e, "device_type", "")).endswith("CUDA")
+                           and not e.key.startswith(("Optimizer.", "ProfilerStep", "aten::", "autograd::"))), key=lambda r: -r[1])
             with open(profile_path, "w") as f:
                 json.dump({"impl": "torch-gpu", "ms_per_step": ms, "kernels_us_per_step":
-                           [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:40]]},
+                           [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:160]]},
                           f, indent=1)
         barrier()
     if with_e2e:
@@ -778,10 +779,11 @@ def main_b200(args, rank, local_rank, world):
             torch.cuda.synchronize()
         if rank == 0:
             rows = sorted(((e.key, e.device_time_total / 5.0, e.count / 5.0) for e in prof.key_averages()
-                           if e.device_time_total > 0 and str(getattr(e, "device_type", "")).endswith("CUDA")), key=lambda r: -r[1])
+                           if e.device_time_total > 0 and str(getattr(e, "device_type", "")).endswith("CUDA")
+                           and not e.key.startswith(("Optimizer.", "ProfilerStep", "aten::", "autograd::"))), key=lambda r: -r[1])
             with open(args.profile, "w") as f:
                 json.dump({"impl": "b200", "ms_per_step": total_ms / K, "kernels_us_per_step":
-                           [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:40]]},
+                           [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:160]]},
                           f, indent=1)
             log(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25))
     barrier()
@@ -861,10 +863,11 @@ def main_b200(args, rank, local_rank, world):
                 worker._pass_one_epoch(host_problem, loaders, Mode.TRAIN)
                 torch.cuda.synchronize()
             rows = sorted(((e.key, e.device_time_total / L, e.count / L) for e in prof.key_averages()
-                           if e.device_time_total > 0 and str(getattr(e, "device_type", "")).endswith("CUDA")), key=lambda r: -r[1])
+                           if e.device_time_total > 0 and str(getattr(e, "device_type", "")).endswith("CUDA")
+                           and not e.key.startswith(("Optimizer.", "ProfilerStep", "aten::", "autograd::"))), key=lambda r: -r[1])
             with open(args.profile.replace(".json", "") + "_e2e.json", "w") as f:
                 json.dump({"impl": "b200 e2e epoch", "steps": L, "kernels_us_per_step":
-                           [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:40]]},
+                           [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:160]]},
                           f, indent=1)
         n_metrics = len(stats[t.Split.TRAIN].metrics)
         e2e = {"value": world * B * e2e_steps / (e2e_ms / 1e3), "unit": "samples/s",

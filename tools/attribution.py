@@ -24,6 +24,8 @@ def grouped(path):
     out = {g: [0.0, 0.0] for g, _ in GROUPS}
     out["unclassified"] = [0.0, 0.0]
     for k in d["kernels_us_per_step"]:
+        if k["name"].startswith(("Optimizer.", "ProfilerStep", "aten::", "autograd::")):
+            continue                      # profiler annotations, not kernels
         for g, pats in GROUPS:
             if any(p in k["name"] for p in pats):
                 out[g][0] += k["us"]
