@@ -5,7 +5,8 @@ same CPU ``torch.randperm`` from a ``torch.Generator`` seeded with the epoch num
 start at 1, reference solver_worker.py:429,785) and then padded and strided exactly as there.
 """
 import math
-from typing import Iterator, List
+import threading
+from typing import Dict, Iterator, List, Optional
 
 import torch
 import torch.utils.data.distributed
@@ -36,6 +37,40 @@ class ScaffoldSampler(torch.utils.data.distributed.DistributedSampler):
         self._shuffle_type = shuffle_type
         self._node_idx = node_idx
         self._node_count = node_count
+        # the global permutation of an epoch depends on the epoch NUMBER only, and every rank needs
+        # the whole of it: at 8 ranks x 4096 samples x 20 steps that is 655 360 draws = 18 ms of
+        # serial Fisher-Yates per rank per epoch.  The next epoch's permutation is therefore drawn
+        # on a helper thread while this epoch trains (same generator seed, same values).
+        self._perm_ready: Dict[int, torch.Tensor] = {}
+        self._perm_thread: Optional[threading.Thread] = None
+
+    def _draw(self, epoch: int, quiet: bool) -> torch.Tensor:
+        gen = torch.Generator()
+        gen.manual_seed(epoch)
+        n = len(self.dataset)
+        if quiet:
+            from .device_loader import randperm_quiet
+            return randperm_quiet(n, gen)
+        return torch.randperm(n, generator=gen)
+
+    def _prefetch(self, epoch: int) -> None:
+        def work() -> None:
+            self._perm_ready[epoch] = self._draw(epoch, quiet=False)
+        self._perm_thread = threading.Thread(target=work, name="frl-perm", daemon=True)
+        self._perm_thread.start()
+
+    def _global_permutation(self, epoch: int) -> torch.Tensor:
+        if self._perm_thread is not None:          # at most one draw is ever outstanding
+            self._perm_thread.join()
+            self._perm_thread = None
+        order = self._perm_ready.pop(epoch, None)
+        if order is None:
+            order = self._draw(epoch, quiet=True)
+        for stale in [e for e in self._perm_ready if e != epoch + 1]:
+            del self._perm_ready[stale]
+        if epoch + 1 not in self._perm_ready:
+            self._prefetch(epoch + 1)
+        return order
 
     def rank_index_tensor(self) -> torch.Tensor:
         """This rank's sample ids of the current epoch as an int64 tensor — what ``__iter__``
@@ -54,9 +89,9 @@ class ScaffoldSampler(torch.utils.data.distributed.DistributedSampler):
             return order[self.rank % ranks_per_node:: ranks_per_node].contiguous()
         if self._shuffle_type != ShuffleType.RANDPERM:
             raise ValueError("Unhandled shuffle type %s", self._shuffle_type)
-        from .device_loader import randperm_quiet
-        order = randperm_quiet(n, gen) if self.shuffle else torch.arange(n)
-        order = torch.cat([order, order[: self.total_size - n]])          # pad with the head
+        order = self._global_permutation(self.epoch) if self.shuffle else torch.arange(n)
+        if self.total_size > n:
+            order = torch.cat([order, order[: self.total_size - n]])      # pad with the head
         assert len(order) == self.total_size
         mine = order[self.rank: self.total_size: self.num_replicas].contiguous()
         assert len(mine) == self.num_samples
