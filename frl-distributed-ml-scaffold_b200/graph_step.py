@@ -40,7 +40,8 @@ def _signature(data: Sequence[torch.Tensor], target) -> Tuple:
 
 
 class GraphedTrainStep:
-    WARMUP_STEPS = 3      # eager steps of a given signature before it is captured
+    WARMUP_STEPS = 2      # eager steps of a given signature before it is captured (cuDNN/cuBLAS
+                          # pick their algorithms on the first call of every shape)
 
     def __init__(self, worker) -> None:
         self.worker = worker

@@ -359,7 +359,7 @@ class Solver:
                 "Linear layers with arena-born gradients %d (%d fused with their ReLU) | other "
                 "gradients %s",
                 args.precision.value,
-                "CUDA-graph replay after 3 eager steps" if worker.graphed is not None else "eager launches",
+                "CUDA-graph replay after 2 eager steps" if worker.graphed is not None else "eager launches",
                 ("fused NVLS kernel per bucket (K7), %d buckets" % len(pipeline.buckets)) if pipeline.nvls is not None
                 else ("ncclAllReduce in place + K2 per bucket, %d buckets" % len(pipeline.buckets)) if distributed
                 else "none (1 GPU)",
@@ -576,7 +576,7 @@ class Solver:
                        ``Precision.BF16`` (bf16 forward/backward/gradients, fp32 master weights and
                        optimizer state — the benchmarked configuration).  None: FRL_B200_PRECISION.
         ``graph``      True: replay the training step from a CUDA graph once a batch signature
-                       has run 3 eager steps (the Problem's forward must be capturable: static
+                       has run 2 eager steps (the Problem's forward must be capturable: static
                        shapes, no host syncs; a failed capture falls back to eager launches).
                        None: FRL_B200_CUDA_GRAPH (default off).
         """

@@ -106,7 +106,7 @@ def _b200(algo, precision, graph, monkeypatch):
                            for s in sorted(worker.arena.slots, key=lambda s: s.index) if s.is_model]
     torch.cuda.synchronize()
     if graph == "1":
-        assert worker.graphed is not None and len(worker.graphed._graphs) == 1   # steps 4.. replayed
+        assert worker.graphed is not None and len(worker.graphed._graphs) == 1   # steps 3.. replayed
     final = [worker.arena.master_view(s).cpu().clone()
              for s in sorted(worker.arena.slots, key=lambda s: s.index) if s.is_model]
     return np.asarray(rows, dtype=np.float64), first_grads, final

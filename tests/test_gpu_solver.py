@@ -184,7 +184,7 @@ def test_multi_gpu_pipeline_matches_oracle(tmp_path):
 
 @pytest.mark.parametrize("name", ["toy_sgd", "toy_adam_clip", "toy_uncertainty"])
 def test_cuda_graph_replay_matches_reference_solver(ns, golden_dir, name, monkeypatch):
-    """Same parity bar with the step replayed from a CUDA graph (captured after 3 eager steps)."""
+    """Same parity bar with the step replayed from a CUDA graph (captured after 2 eager steps)."""
     monkeypatch.setenv("FRL_B200_CUDA_GRAPH", "1")
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     _, worker, problem, save_dir = _solve_and_capture(ns, CONFIGS[name])
