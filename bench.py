@@ -385,7 +385,7 @@ def run_torch_gpu(args, rank, local_rank, world, steps, warmup, with_e2e=True, p
         if rank == 0:
             rows = sorted(((e.key, e.device_time_total / 5.0, e.count / 5.0) for e in prof.key_averages()
                            if e.device_time_total > 0 and str(getattr(e, "device_type", "")).endswith("CUDA")
-                           and not e.key.startswith(("Optimizer.", "ProfilerStep", "aten::", "autograd::"))), key=lambda r: -r[1])
+                           and not e.key.startswith(("Optimizer.", "ProfilerStep", "aten::", "autograd::", "nccl:", "DistributedDataParallel"))), key=lambda r: -r[1])
             with open(profile_path, "w") as f:
                 json.dump({"impl": "torch-gpu", "ms_per_step": ms, "kernels_us_per_step":
                            [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:160]]},
@@ -585,7 +585,11 @@ def nvls_parity_check(worker, step_fn, world, algo, precision):
 
     res = {"what": "one step from identical state and batch: K7 (fused NVLS reduce+update+multicast) "
                    "vs ncclAllReduce + K2, world %d, %s gradients" % (world, "bf16" if precision == "bf16" else "fp32"),
-           "master": rel(a_master, b_master)}
+           "master": rel(a_master, b_master),
+           # how far that one step moved the weights (so a difference of 0 is not "nothing happened";
+           # at world 8 NCCL itself reduces in the NVSwitch and the two paths can agree bit for bit)
+           "step_moved_master_rel_l2": float((a_master.double() - saved["master"].double()).norm()
+                                             / saved["master"].double().norm().clamp_min(1e-30))}
     if a_state is not None:
         res["state:" + names[0]] = rel(a_state, b_state)
     # bounds: the update moves a weight by lr x (reduced gradient); the two reductions differ by
@@ -780,7 +784,7 @@ def main_b200(args, rank, local_rank, world):
         if rank == 0:
             rows = sorted(((e.key, e.device_time_total / 5.0, e.count / 5.0) for e in prof.key_averages()
                            if e.device_time_total > 0 and str(getattr(e, "device_type", "")).endswith("CUDA")
-                           and not e.key.startswith(("Optimizer.", "ProfilerStep", "aten::", "autograd::"))), key=lambda r: -r[1])
+                           and not e.key.startswith(("Optimizer.", "ProfilerStep", "aten::", "autograd::", "nccl:", "DistributedDataParallel"))), key=lambda r: -r[1])
             with open(args.profile, "w") as f:
                 json.dump({"impl": "b200", "ms_per_step": total_ms / K, "kernels_us_per_step":
                            [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:160]]},
@@ -864,7 +868,7 @@ def main_b200(args, rank, local_rank, world):
                 torch.cuda.synchronize()
             rows = sorted(((e.key, e.device_time_total / L, e.count / L) for e in prof.key_averages()
                            if e.device_time_total > 0 and str(getattr(e, "device_type", "")).endswith("CUDA")
-                           and not e.key.startswith(("Optimizer.", "ProfilerStep", "aten::", "autograd::"))), key=lambda r: -r[1])
+                           and not e.key.startswith(("Optimizer.", "ProfilerStep", "aten::", "autograd::", "nccl:", "DistributedDataParallel"))), key=lambda r: -r[1])
             with open(args.profile.replace(".json", "") + "_e2e.json", "w") as f:
                 json.dump({"impl": "b200 e2e epoch", "steps": L, "kernels_us_per_step":
                            [{"name": k[:120], "us": round(us, 2), "launches": round(n, 2)} for k, us, n in rows[:160]]},

@@ -24,7 +24,7 @@ def grouped(path):
     out = {g: [0.0, 0.0] for g, _ in GROUPS}
     out["unclassified"] = [0.0, 0.0]
     for k in d["kernels_us_per_step"]:
-        if k["name"].startswith(("Optimizer.", "ProfilerStep", "aten::", "autograd::")):
+        if k["name"].startswith(("Optimizer.", "ProfilerStep", "aten::", "autograd::", "nccl:", "DistributedDataParallel")):
             continue                      # profiler annotations, not kernels
         for g, pats in GROUPS:
             if any(p in k["name"] for p in pats):
