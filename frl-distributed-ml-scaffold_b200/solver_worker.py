@@ -623,6 +623,11 @@ def _gc_paused():
     finally:
         if pause:
             gc.enable()
+            if os.environ.get("FRL_B200_EPOCH_TRACE"):
+                t0 = time.perf_counter()
+                n = gc.collect()
+                logger.info("gc trace: explicit collection after the loop: %.2f ms, %d unreachable, %d tracked objects",
+                            1e3 * (time.perf_counter() - t0), n, len(gc.get_objects()))
 
 
 class SolverWorker:
@@ -790,9 +795,13 @@ class SolverWorker:
                 while checked < n_batches:
                     self._raise_if_nan(log, checked, data_type)
                     checked += 1
+                mark("nan guard done")
                 if not fold_early:           # host-returning hooks: after the NaN guard, as before
                     sampler_state.compute_metrics()
+                    mark("last window folded (late)")
                 sampler_state.finish()
+                mark("finish done")
+            mark("loop context exited")
             timer.epoch.update(time.time() - epoch_start)
 
             per_step = log.rows[:n_batches].numpy()
