@@ -507,6 +507,7 @@ class SamplerState:
                     "output": [host(x) for x in p["output"]],
                     "score": host(p["score"]) if "score" in p else None}
 
+        t_begin = time.perf_counter()
         n = self._cur_samples
         cols_h = {k: host(v[:n]) for k, v in self._dev_cols.items()}
         meta_h = {k: host(v[:n]) for k, v in self._dev_meta.items()}
@@ -518,9 +519,10 @@ class SamplerState:
         torch.cuda.current_stream(self._device).synchronize()
         t_s = time.perf_counter()
         pending.clear()
-        if os.environ.get("FRL_B200_EPOCH_TRACE"):
-            logger.info("finish trace: %d tensors queued, flush issued in %.2f ms, sync waited %.2f ms",
-                        len(requests), 1e3 * (t_f - t_q), 1e3 * (t_s - t_f))
+        tracing = bool(os.environ.get("FRL_B200_EPOCH_TRACE"))
+        if tracing:
+            logger.info("finish trace: %d tensors queued (built in %.2f ms), flush issued in %.2f ms, sync waited %.2f ms",
+                        len(requests), 1e3 * (t_q - t_begin), 1e3 * (t_f - t_q), 1e3 * (t_s - t_f))
 
         def resolve(x):
             if isinstance(x, int):
@@ -562,6 +564,8 @@ class SamplerState:
             order = sorted(range(len(kept)), key=lambda i: kept_scores[i])
             self._worst_samples = [(kept_scores[i], kept[i]) for i in order]
         self._dev_random, self._dev_worst = [], None
+        if tracing:
+            logger.info("finish trace: host-side assembly after the sync %.2f ms", 1e3 * (time.perf_counter() - t_s))
 
     @property
     def n_samples(self) -> int:
