@@ -520,9 +520,14 @@ class SamplerState:
         t_s = time.perf_counter()
         pending.clear()
         tracing = bool(os.environ.get("FRL_B200_EPOCH_TRACE"))
+        prof = None
         if tracing:
             logger.info("finish trace: %d tensors queued (built in %.2f ms), flush issued in %.2f ms, sync waited %.2f ms",
                         len(requests), 1e3 * (t_q - t_begin), 1e3 * (t_f - t_q), 1e3 * (t_s - t_f))
+            if os.environ.get("FRL_B200_EPOCH_TRACE") == "profile":
+                import cProfile
+                prof = cProfile.Profile()
+                prof.enable()
 
         def resolve(x):
             if isinstance(x, int):
@@ -566,6 +571,13 @@ class SamplerState:
         self._dev_random, self._dev_worst = [], None
         if tracing:
             logger.info("finish trace: host-side assembly after the sync %.2f ms", 1e3 * (time.perf_counter() - t_s))
+        if prof is not None:
+            import io as _io
+            import pstats
+            prof.disable()
+            out = _io.StringIO()
+            pstats.Stats(prof, stream=out).sort_stats("cumulative").print_stats(14)
+            logger.info("finish profile:\n%s", out.getvalue())
 
     @property
     def n_samples(self) -> int:
