@@ -539,10 +539,16 @@ class SamplerState:
             return x
 
         cols_h, meta_h, random_h, worst_h = resolve(cols_h), resolve(meta_h), resolve(random_h), resolve(worst_h)
+        def own(t: torch.Tensor) -> torch.Tensor:
+            # a PAGEABLE copy out of the staging block: ``clone()`` of a pinned tensor allocates
+            # pinned memory again (empty_like keeps the option) — a cudaHostAlloc per call, measured
+            # at 6 ms each
+            return torch.empty(t.shape, dtype=t.dtype).copy_(t)
+
         cols = {k: v.numpy().copy() for k, v in cols_h.items()}
         for k, v in cols.items():
             self._data_metric[k] = [v]
-        dev_meta = {k: v.clone() for k, v in meta_h.items()}
+        dev_meta = {k: own(v) for k, v in meta_h.items()}
 
         def samples_of(p, keep=None) -> List[SingleSample]:
             out = []
@@ -551,9 +557,9 @@ class SamplerState:
                     continue
                 meta = {k: v[g] for k, v in dev_meta.items()}
                 meta.update({k: v[g] for k, v in self._host_meta.items()})
-                out.append(SingleSample(data=[x[r].clone() for x in p["data"]],
-                                        target=[tuple(x[r].clone() for x in h) for h in p["target"]],
-                                        meta=meta, output=[x[r].clone() for x in p["output"]],
+                out.append(SingleSample(data=[own(x[r]) for x in p["data"]],
+                                        target=[tuple(own(x[r]) for x in h) for h in p["target"]],
+                                        meta=meta, output=[own(x[r]) for x in p["output"]],
                                         metric={k: cols[k][g] for k in cols}))
             return out
 
