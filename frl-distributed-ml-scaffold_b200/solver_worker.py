@@ -540,10 +540,12 @@ class SamplerState:
 
         cols_h, meta_h, random_h, worst_h = resolve(cols_h), resolve(meta_h), resolve(random_h), resolve(worst_h)
         def own(t: torch.Tensor) -> torch.Tensor:
-            # a PAGEABLE copy out of the staging block: ``clone()`` of a pinned tensor allocates
-            # pinned memory again (empty_like keeps the option) — a cudaHostAlloc per call, measured
-            # at 6 ms each
-            return torch.empty(t.shape, dtype=t.dtype).copy_(t)
+            # a pageable copy out of the staging block by plain memcpy.  ``clone()``/``copy_`` of a
+            # CPU tensor above ATen's grain size (32 768 elements) is an OpenMP parallel region:
+            # waking a 128-thread pool that sleeps between epochs was measured at 4-6 ms PER CALL
+            # (13 calls = 58-76 ms per ResNet epoch); numpy's copy is single-threaded and takes
+            # 0.15 ms for a 600 KB image
+            return torch.from_numpy(t.numpy().copy())
 
         cols = {k: v.numpy().copy() for k, v in cols_h.items()}
         for k, v in cols.items():
