@@ -70,11 +70,7 @@ class _ArenaLinearFn(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1])
         pipe = site.pipeline
         if pipe is not None and pipe.step_open:
-            gw = pipe.arena.grad_view(site.wslot)
-            if site.wstate.first_touch(pipe.step_id):
-                torch.mm(dy2.t(), x2, out=gw)
-            else:
-                gw.addmm_(dy2.t(), x2)
+            site.weight_grad(pipe, dy2, x2)
             if ctx.has_bias and site.bslot is not None:
                 if not dy2.is_contiguous():
                     dy2 = dy2.contiguous()
@@ -117,11 +113,7 @@ class _ArenaLinearReluFn(torch.autograd.Function):
                                  accumulate=not site.bstate.first_touch(pipe.step_id))
             # dX before any slot is marked ready (the bucket's update overwrites W)
             dx = dz.matmul(weight).view_as(x) if ctx.needs_input_grad[0] else None
-            gw = pipe.arena.grad_view(site.wslot)
-            if site.wstate.first_touch(pipe.step_id):
-                torch.mm(dz.t(), x2, out=gw)
-            else:
-                gw.addmm_(dz.t(), x2)
+            site.weight_grad(pipe, dz, x2)
             site.backward_done(pipe)
             return dx, None, None, None
         dz = dy2 * (y2 > 0).to(dy2.dtype)
@@ -297,6 +289,24 @@ class LinearSite:
         states = pipeline.slot_states
         self.wstate = states.setdefault(wslot.index, SlotState())
         self.bstate = states.setdefault(bslot.index, SlotState()) if bslot is not None else None
+
+    def weight_grad(self, pipe, dz: torch.Tensor, x2: torch.Tensor) -> None:
+        """dW = dZ^T X into the weight's arena slice (store on the step's first touch, accumulate
+        after).  A weight the pipeline exchanges in two row blocks (``row_split``: the layer whose
+        dW ends backward) is computed as two GEMMs and the first block handed over in between,
+        provided this is the parameter's only application in the step."""
+        gw = pipe.arena.grad_view(self.wslot)
+        st = self.wstate
+        if not st.first_touch(pipe.step_id):
+            gw.addmm_(dz.t(), x2)
+            return
+        rows = pipe.row_split(self.wslot)
+        if rows and st.fwd_gen == pipe.forward_gen and st.fwd_count == 1:
+            torch.mm(dz[:, :rows].t(), x2, out=gw[:rows])
+            pipe.rows_ready(self.wslot, rows)
+            torch.mm(dz[:, rows:].t(), x2, out=gw[rows:])
+        else:
+            torch.mm(dz.t(), x2, out=gw)
 
     def count_forward(self) -> None:
         pipe = self.pipeline

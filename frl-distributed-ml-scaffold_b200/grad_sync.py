@@ -99,17 +99,39 @@ class GradBucketPipeline:
             for lo, hi in ranges:
                 split += [(cut, hi), (lo, cut)] if lo < cut < hi else [(lo, hi)]
             ranges = split
+        # Tail split.  The bucket that becomes ready LAST (the first layer's weight: its dW GEMM is
+        # the final kernel of backward) is the only one whose exchange cannot hide behind backward
+        # work.  When that bucket starts with a large 2-D weight, the weight's rows are cut in two
+        # buckets: the layer computes dW as two row-block GEMMs and hands over the first half
+        # (``rows_ready``) while the second is still running, so only half of the exchange is
+        # exposed.  The cut is STATIC (decided here, not per step): with the fused NVLS step the
+        # launch ranges define which rank owns which shard of the master weights and state.
+        self._row_split: Dict[int, int] = {}            # slot.index -> rows in the first half
+        min_bytes = int(os.environ.get("FRL_B200_TAIL_SPLIT_MIN_BYTES", str(4 << 20)))
+        if (self.distributed and self.eager and ranges
+                and os.environ.get("FRL_B200_TAIL_SPLIT", "1") != "0"):
+            lo, hi = ranges[-1]
+            esz = 2 if arena.grad_dtype == torch.bfloat16 else 4
+            head = next((s for s in arena.slots if s.offset == lo), None)
+            if (head is not None and len(head.shape) == 2 and head.end <= hi
+                    and head.shape[0] >= 2 and (head.end - lo) * esz >= min_bytes
+                    and 2 * (head.end - lo) >= hi - lo):
+                rows = head.shape[0] // 2
+                if (rows * head.shape[1]) % 8 == 0:       # launch ranges stay 8-element aligned
+                    mid = lo + rows * head.shape[1]
+                    ranges = ranges[:-1] + [(lo, mid), (mid, hi)]
+                    self._row_split[head.index] = rows
         self.buckets: List[_Bucket] = [_Bucket(lo, hi) for lo, hi in ranges]
         if use_nvls and arena.lp is not None:
             for b in self.buckets:
                 b.replicated = b.lo >= arena.model_end
-        self._bucket_of = {}
+        self._buckets_of: Dict[int, List[_Bucket]] = {}
         for s in arena.slots:
-            for b in self.buckets:
-                if b.lo <= s.offset < b.hi:
+            for b in self.buckets:                   # launch order; a row-split slot is in two
+                inside = (s.offset < b.hi and s.end > b.lo) if s.end > s.offset else (b.lo <= s.offset < b.hi)
+                if inside:
                     b.slots.append(s)
-                    self._bucket_of[id(s.param)] = b
-                    break
+                    self._buckets_of.setdefault(id(s.param), []).append(b)
         self._n_slots = len(arena.slots)
         self._ready = 0
         self._ready_ids = set()
@@ -228,10 +250,28 @@ class GradBucketPipeline:
             return
         self._ready_ids.add(id(slot.param))
         self._ready += 1
-        b = self._bucket_of[id(slot.param)]
-        b.pending -= 1
-        if b.pending == 0 and (self.distributed or self.eager):
-            self._launch_bucket(b)
+        for b in self._buckets_of[id(slot.param)]:
+            if b.launched:                    # the first half of a row-split weight went ahead
+                continue
+            b.pending -= 1
+            if b.pending == 0 and (self.distributed or self.eager):
+                self._launch_bucket(b)
+
+    def row_split(self, slot) -> int:
+        """Rows of the slot's first half if its weight gradient is exchanged in two row blocks
+        (tail split, see ``__init__``), else 0."""
+        return self._row_split.get(slot.index, 0)
+
+    def rows_ready(self, slot, rows: int) -> None:
+        """Rows ``[0, rows)`` of the slot's gradient are final and the rest is still being
+        computed: launch every bucket that lies inside them and waits for nothing else."""
+        if not self._step_open:
+            return
+        done = slot.offset + rows * slot.shape[1]
+        for b in self._buckets_of[id(slot.param)]:
+            if not b.launched and b.hi <= done and b.pending == 1:
+                b.pending = 0
+                self._launch_bucket(b)
 
     def defer_ready(self, slot) -> None:
         """The slot's gradient was written but more contributions are expected in this backward;

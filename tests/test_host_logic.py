@@ -438,6 +438,87 @@ def test_reused_and_tied_linears_wait_for_their_last_gradient(tmp_path, patched)
         np.testing.assert_allclose(a.numpy(), b.detach().numpy(), rtol=2e-5, atol=2e-7)
 
 
+# ---- tail split: the weight whose dW ends backward is exchanged in two row blocks --------------------
+
+class _TailNet(nn.Module):
+    def __init__(self, seed, twice):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.first = nn.Sequential(nn.Linear(8, 16), nn.ReLU())
+        self.mid = nn.Linear(16, 8)
+        self.head = nn.Linear(8, 2)
+        self.twice = twice
+
+    def forward(self, x):
+        h = self.first(x)
+        if self.twice:                       # second application of `first`: no early hand-over
+            h = self.first(torch.relu(self.mid(h)))
+        return self.head(torch.relu(self.mid(h)))
+
+
+def _tail_rank_main(rank, world, port, mode, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["FRL_B200_TAIL_SPLIT_MIN_BYTES"] = "0"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from frl_b200 import arena_linear
+    d = KernelDouble()
+    fused_optim.KERNELS = d
+    grad_sync.KERNELS = d
+    arena_linear.KERNELS = d
+    net = _TailNet(4, twice=(mode == "twice"))
+    arena = ParamArena(net.parameters(), device="cpu")
+    opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm.SGD, lr=0.05))
+    pipe = grad_sync.GradBucketPipeline(arena, opt, world_size=world, bucket_cap_mb=0.0001,
+                                        first_bucket_mb=0.00005, eager_update=True)
+    first_w = arena.slots[0]
+    assert tuple(first_w.shape) == (16, 8) and pipe.row_split(first_w) == 8
+    a, b = pipe.buckets[-2], pipe.buckets[-1]
+    assert (a.lo, a.hi) == (0, 64) and b.lo == 64 and a.slots == [first_w] and first_w in b.slots
+    if mode != "hooks":
+        pipe.patch_linears(net)
+    launches = []
+    inner = pipe._launch_bucket
+    pipe._launch_bucket = lambda bk: (launches.append((bk.lo, bk.hi, pipe._ready)), inner(bk))[1]
+    pipe.broadcast_parameters(src=0)
+    g = torch.Generator().manual_seed(5)
+    net.train()
+    for step in range(3):
+        x = torch.randn(8 * world, 8, generator=g)
+        out = net(x[rank::world])
+        pipe.begin_step()
+        del launches[:]
+        out.square().mean().backward()
+        pipe.finish_step()
+        order = [l[:2] for l in launches]
+        ia, ib = order.index((0, 64)), order.index((64, b.hi))
+        assert ia < ib and len(order) == len(pipe.buckets)
+        early = launches[ia][2] < launches[ib][2]        # first half went before the slot was ready
+        assert early == (mode == "once"), (mode, launches)
+    torch.save([p.detach().clone() for p in net.parameters()], os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["once", "twice", "hooks"])
+def test_tail_split_hands_over_the_first_row_block_early(tmp_path, mode):
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_tail_rank_main, args=(world, port, mode, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
+    for a, b in zip(r0, r1):
+        assert torch.equal(a, b)
+    ref = _TailNet(4, twice=(mode == "twice"))
+    ref_opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-5)
+    g = torch.Generator().manual_seed(5)
+    for step in range(3):
+        x = torch.randn(8 * world, 8, generator=g)
+        ref_opt.zero_grad()
+        ref(x).square().mean().backward()
+        ref_opt.step()
+    for a, b in zip(r0, ref.parameters()):
+        np.testing.assert_allclose(a.numpy(), b.detach().numpy(), rtol=2e-5, atol=2e-7)
+
+
 # ---- round-2 host logic: arena layout groups, bucket merging, quiet randperm, multi-head unit ------
 
 def test_adjacent_groups_keep_parameter_positions_and_sorted_offsets():
