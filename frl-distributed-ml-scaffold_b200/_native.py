@@ -72,6 +72,7 @@ SIGNATURES = {
     "frl_drelu_colsum": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _i, _i, _vp, _vp]),
     "frl_gather_rows": (_i, [_vp, _i64, _vp, _vp, _i64, _i64, _i, _vp]),
     "frl_gather_rows_tma": (_i, [_vp, _i64, _vp, _vp, _i64, _i64, _i, _vp]),
+    "frl_gather_window_rows": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _i64, _vp]),
     "frl_gather_pool_create": (_vp, [_i]),
     "frl_gather_pool_destroy": (None, [_vp]),
     "frl_gather_pool_threads": (_i, [_vp]),
@@ -354,6 +355,24 @@ def gather_rows_tma(src_pinned, idx_dev, dst, max_blocks: int = 0) -> None:
     _check(lib().frl_gather_rows_tma(_ptr(src_pinned), src_pinned.shape[0], _ptr(idx_dev), _ptr(dst),
                                      idx_dev.numel(), _row_bytes(src_pinned), max_blocks, _stream()),
            "frl_gather_rows_tma")
+
+
+def gather_window_rows(batches, idx_dev, dst=None):
+    """Rows ``idx_dev`` (device int64, numbered through the concatenation of ``batches``) of a
+    list of separate device tensors [rows_b, ...] with one row shape, without concatenating them."""
+    first = batches[0]
+    assert all(b.is_cuda and b.is_contiguous() and b.shape[1:] == first.shape[1:] and b.dtype == first.dtype
+               for b in batches) and idx_dev.dtype == torch.int64 and idx_dev.is_cuda
+    if dst is None:
+        dst = torch.zeros((idx_dev.numel(),) + tuple(first.shape[1:]), dtype=first.dtype, device=first.device)
+    n = len(batches)
+    ptrs = (C.c_void_p * n)(*[b.data_ptr() for b in batches])
+    rows = (C.c_int64 * n)(*[b.shape[0] for b in batches])
+    row_bytes = first[0].numel() * first.element_size() if first.shape[0] else \
+        (int(torch.tensor(first.shape[1:]).prod()) * first.element_size())
+    _check(lib().frl_gather_window_rows(ptrs, rows, n, _ptr(idx_dev), _ptr(dst), idx_dev.numel(), row_bytes,
+                                        _stream()), "frl_gather_window_rows")
+    return dst
 
 
 class HostGatherPool:

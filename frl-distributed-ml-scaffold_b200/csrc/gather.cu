@@ -168,6 +168,37 @@ static void launch_small(const void* src, const int64_t* idx, void* dst, int64_t
         static_cast<const U*>(src), idx, static_cast<U*>(dst), n_rows, upr, src_rows);
 }
 
+
+// K8w — rows of a WINDOW of retained minibatches: the source is a list of separate device
+// tensors (batch b holds window rows [starts[b], starts[b+1])), the row numbers come out of a
+// device top-k, so neither the host nor a single base pointer can address them.  The table of
+// batch pointers travels in the kernel's parameter block (no upload, capturable); one CTA per
+// picked row, 16-byte units when everything is aligned, bytes otherwise.
+constexpr int kWindowMax = 64;
+struct WindowTable {
+    const uint8_t* base[kWindowMax];
+    int64_t start[kWindowMax + 1];
+    int n;
+};
+
+__global__ void __launch_bounds__(kGThreads)
+gather_window_rows_kernel(const WindowTable tab, const int64_t* __restrict__ idx, uint8_t* __restrict__ dst,
+                          int64_t row_bytes, int wide) {
+    const int64_t r = blockIdx.x;
+    const int64_t want = __ldg(idx + r);
+    if (want < tab.start[0] || want >= tab.start[tab.n]) return;      // not in this table: leave dst
+    int b = 0;
+    while (b + 1 < tab.n && want >= tab.start[b + 1]) ++b;
+    const uint8_t* from = tab.base[b] + (want - tab.start[b]) * row_bytes;
+    uint8_t* to = dst + r * row_bytes;
+    if (wide) {
+        const int4* f16 = reinterpret_cast<const int4*>(from);
+        int4* t16 = reinterpret_cast<int4*>(to);
+        for (int64_t u = threadIdx.x; u < (row_bytes >> 4); u += kGThreads) t16[u] = __ldg(f16 + u);
+    } else {
+        for (int64_t u = threadIdx.x; u < row_bytes; u += kGThreads) to[u] = from[u];
+    }
+}
 }  // namespace frl
 
 using namespace frl;
@@ -207,6 +238,34 @@ extern "C" int frl_gather_rows(const void* src_mapped, int64_t src_rows, const i
     return after_launch("frl_gather_rows");
 }
 
+
+
+extern "C" int frl_gather_window_rows(const void* const* batch_ptrs, const int64_t* batch_rows, int n_batches,
+                                      const int64_t* idx_dev, void* dst, int64_t n_rows, int64_t row_bytes,
+                                      void* stream) {
+    FRL_REQUIRE(n_batches >= 0 && n_rows >= 0 && row_bytes >= 0, FRL_E_ARG, "frl_gather_window_rows: sizes");
+    if (n_rows == 0 || row_bytes == 0 || n_batches == 0) return 0;
+    FRL_REQUIRE(batch_ptrs && batch_rows && idx_dev && dst, FRL_E_ARG, "frl_gather_window_rows: null pointer");
+    FRL_REQUIRE(n_rows < (1ll << 31), FRL_E_ARG, "frl_gather_window_rows: too many rows");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int64_t first = 0;
+    for (int lo = 0; lo < n_batches; lo += kWindowMax) {              // tables of at most 64 batches
+        WindowTable tab;
+        tab.n = n_batches - lo < kWindowMax ? n_batches - lo : kWindowMax;
+        uintptr_t bits = reinterpret_cast<uintptr_t>(dst) | static_cast<uintptr_t>(row_bytes);
+        tab.start[0] = first;
+        for (int b = 0; b < tab.n; ++b) {
+            FRL_REQUIRE(batch_ptrs[lo + b] && batch_rows[lo + b] >= 0, FRL_E_ARG, "frl_gather_window_rows: batch %d", lo + b);
+            tab.base[b] = static_cast<const uint8_t*>(batch_ptrs[lo + b]);
+            tab.start[b + 1] = tab.start[b] + batch_rows[lo + b];
+            bits |= reinterpret_cast<uintptr_t>(batch_ptrs[lo + b]);
+        }
+        first = tab.start[tab.n];
+        gather_window_rows_kernel<<<static_cast<int>(n_rows), kGThreads, 0, st>>>(
+            tab, idx_dev, static_cast<uint8_t*>(dst), row_bytes, (bits & 15u) == 0 ? 1 : 0);
+    }
+    return after_launch("frl_gather_window_rows");
+}
 
 // TMA (cp.async.bulk) variant of frl_gather_rows: rows must be multiples of 16 bytes.
 extern "C" int frl_gather_rows_tma(const void* src_mapped, int64_t src_rows, const int64_t* idx_dev,

@@ -384,21 +384,13 @@ class SamplerState:
     @staticmethod
     def _gather_rows(batches: List[torch.Tensor], starts: List[int], idx: torch.Tensor) -> torch.Tensor:
         """Rows ``idx`` (device int64, window-relative) of the retained minibatch list.  The host
-        does not know ``idx`` (it comes out of a device ``topk``), so the window is concatenated
-        once (a device copy of at most a few hundred MB per amortisation window: ~0.1 ms, two
-        launches) unless it is too large, in which case every minibatch is probed (4 launches
-        each)."""
-        if sum(b.numel() * b.element_size() for b in batches) <= (1 << 30):
-            return (batches[0] if len(batches) == 1 else torch.cat(batches)).index_select(0, idx)
-        out = None
-        for b, start in zip(batches, starts):
-            rows = b.index_select(0, (idx - start).clamp_(0, len(b) - 1))
-            if out is None:
-                out = rows
-            else:
-                inside = ((idx >= start) & (idx < start + len(b))).view(-1, *([1] * (rows.dim() - 1)))
-                out = torch.where(inside, rows, out)
-        return out
+        does not know ``idx`` (it comes out of a device ``topk``) and the minibatches are separate
+        tensors: K8w (``frl_gather_window_rows``) walks a table of their base pointers — one launch,
+        only the picked rows move (concatenating the window first was a 0.3 GB device copy per
+        amortisation window at batch 4096 x 4096 bf16, twice: random picks and worst-k)."""
+        if batches[0].is_cuda:
+            return _native.gather_window_rows([b if b.is_contiguous() else b.contiguous() for b in batches], idx)
+        return (batches[0] if len(batches) == 1 else torch.cat(batches)).index_select(0, idx)
 
     def _pick(self, idx: torch.Tensor, data_batches, starts, target, output, meta, sample_metric):
         """Rows ``idx`` (window-relative, device) of everything a ``SingleSample`` shows; metrics

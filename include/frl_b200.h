@@ -269,6 +269,16 @@ int frl_nvls_rmsprop(float* p, float* sq, float* buf, const void* mc_g, void* mc
  * ---------------------------------------------------------------------------------------- */
 int frl_gather_rows(const void* src_mapped, int64_t src_rows, const int64_t* idx_dev, void* dst,
                     int64_t n_rows, int64_t row_bytes, int max_blocks, void* stream);
+/* K8w — rows of a window of retained minibatches (device tensors that are NOT contiguous with
+ * one another): window row w lives in batch b at row w - sum(batch_rows[:b]).  dst[i, :] = that
+ * row for w = idx_dev[i]; rows whose index is outside the window are left untouched.  Replaces
+ * the per-sample slicing of retained minibatches in the loop's SamplerState (reference
+ * solver_worker.py:254-262, 321-351: random picks and the worst-k heap keep data[i] slices)
+ * where the indices only exist on the device.  batch_ptrs / batch_rows are HOST arrays (copied
+ * into the kernel's parameter block, 64 batches per launch); idx_dev int64 [n_rows] on the device. */
+int frl_gather_window_rows(const void* const* batch_ptrs, const int64_t* batch_rows, int n_batches,
+                           const int64_t* idx_dev, void* dst, int64_t n_rows, int64_t row_bytes,
+                           void* stream);
 /* Same contract, moved by the SMs' bulk-copy engine (cp.async.bulk: host -> shared memory -> HBM,
  * one elected thread per CTA, 8 x 16 KB stages in flight).  Rows and pointers must be multiples
  * of 16 bytes.  max_blocks <= 0 -> one CTA per SM. */

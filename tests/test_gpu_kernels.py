@@ -452,6 +452,27 @@ def test_gather_rows_from_pinned_host_memory(rows, cols, dt):
     assert torch.equal(out.cpu(), src[[0, 0]])
 
 
+@pytest.mark.parametrize("sizes,tail,dt", [([64, 64, 17], (4096,), torch.bfloat16), ([5], (3,), torch.float32),
+                                           ([8, 1, 30], (3, 7, 5), torch.uint8), ([4] * 150, (16,), torch.int64),
+                                           ([33, 2], (), torch.float32)])
+def test_window_gather_matches_index_select_of_the_concatenation(sizes, tail, dt):
+    """K8w: picked rows of a list of separate device tensors == index_select on their cat (bit-exact);
+    ragged batches, > 64 batches (several tables), unaligned rows, 1-D batches, rows outside the
+    window left untouched."""
+    torch.manual_seed(sum(sizes))
+    batches = [(torch.randn(n, *tail, device=DEV) * 50).to(dt) for n in sizes]
+    if dt == torch.uint8 and len(sizes) == 3:
+        batches[1] = torch.cat([batches[1].new_zeros(1, *tail), batches[1]])[1:]     # odd base address
+    total = sum(sizes)
+    idx = torch.randint(0, total, (19,), dtype=torch.int64, device=DEV)
+    idx[0], idx[1] = 0, total - 1
+    got = _native.gather_window_rows(batches, idx)
+    assert got.shape == (19,) + tuple(tail) and torch.equal(got, torch.cat(batches).index_select(0, idx))
+    dst = torch.full((3,) + tuple(tail), 7, dtype=dt, device=DEV)
+    out = _native.gather_window_rows(batches, torch.tensor([total, -1, 1 % total], device=DEV), dst)
+    assert torch.equal(out[:2], torch.full_like(out[:2], 7)) and torch.equal(out[2], torch.cat(batches)[1 % total])
+
+
 @pytest.mark.parametrize("rows,cols,dt,blocks", [(1000, 4096, torch.float32, 0), (257, 4096, torch.float32, 3),
                                                  (64, 8, torch.int64, 1), (33, 1024, torch.bfloat16, 2),
                                                  (300, 4096 + 8, torch.float32, 4), (40, 3 * 224 * 224, torch.uint8, 5),
