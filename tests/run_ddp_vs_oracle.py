@@ -54,6 +54,11 @@ def main():
         pipe = grad_sync.GradBucketPipeline(arena, opt, world_size=world, clip_norm=clip,
                                             bucket_cap_mb=0.02, first_bucket_mb=0.005, nvls_link=link)
         assert (pipe.nvls is not None) == bool(nvls)
+        if pipe._row_split:          # FRL_B200_TAIL_SPLIT_MIN_BYTES=0: the split + early hand-over path
+            pipe.patch_linears(model)
+            if rank == 0:
+                print("TAIL_SPLIT rows", dict(pipe._row_split), "buckets",
+                      [(b.lo, b.hi) for b in pipe.buckets[-2:]], flush=True)
         pipe.broadcast_parameters(0)
         assert len(pipe.buckets) >= 3
         g = torch.Generator().manual_seed(7)
