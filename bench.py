@@ -932,8 +932,10 @@ def main_b200(args, rank, local_rank, world):
     elif nv is not None:
         grad_sync_desc = ("fused per-bucket NVLS kernel over NVSwitch multicast (multimem.ld_reduce of the "
                           "bf16 grads + sharded update + multimem.st of the new weights), %d buckets, "
-                          "%d CTAs, barriers %s" % (len(worker.pipeline.buckets), nv.max_blocks,
-                                                    "as separate 1-CTA launches" if nv.flags & 1 else "in-kernel"))
+                          "%d CTAs (%d for the last, exposed bucket), barriers %s, tail split %s"
+                          % (len(worker.pipeline.buckets), nv.max_blocks, nv.tail_blocks,
+                             "as separate 1-CTA launches" if nv.flags & 1 else "in-kernel",
+                             "on" if worker.pipeline._row_split else "off"))
     else:
         grad_sync_desc = "NCCL all-reduce in place on bf16 arena buckets + fused update per bucket"
     if rank == 0:

@@ -125,6 +125,7 @@ class GradBucketPipeline:
         if use_nvls and arena.lp is not None:
             for b in self.buckets:
                 b.replicated = b.lo >= arena.model_end
+        self._last_bucket = self.buckets[-1] if self.buckets else None      # last in launch order
         self._buckets_of: Dict[int, List[_Bucket]] = {}
         for s in arena.slots:
             for b in self.buckets:                   # launch order; a row-split slot is in two
@@ -290,7 +291,14 @@ class GradBucketPipeline:
             if self._ext:
                 self._flatten_stragglers(b.slots, id(b), side=self.on_cuda)
             if self.nvls is not None and not b.replicated:
-                self._update(b.lo, b.hi, None)        # K7: reduce + update + broadcast
+                nv = self.nvls
+                grid = nv.max_blocks
+                if b is self._last_bucket:            # runs alone: backward has nothing left to issue
+                    nv.max_blocks = nv.tail_blocks
+                try:
+                    self._update(b.lo, b.hi, None)    # K7: reduce + update + broadcast
+                finally:
+                    nv.max_blocks = grid
             elif self.distributed:
                 b.work = dist.all_reduce(self.arena.grad[b.lo:b.hi], op=dist.ReduceOp.SUM,
                                          group=self.pg, async_op=True)

@@ -324,7 +324,8 @@ class Solver:
             default_blocks = 74 if args.world_size <= 2 else 16
             nvls_link = make_link(symm_alloc, arena.grad,
                                   arena.lp if arena.lp is not None else arena.master,
-                                  max_blocks=int(os.environ.get("FRL_B200_NVLS_BLOCKS", default_blocks)))
+                                  max_blocks=int(os.environ.get("FRL_B200_NVLS_BLOCKS", default_blocks)),
+                                  tail_blocks=int(os.environ.get("FRL_B200_NVLS_TAIL_BLOCKS", "0")))
         pipeline = GradBucketPipeline(
             arena, optimizer, world_size=args.world_size, clip_norm=run_opts.optim.gradientClip,
             nvls_link=nvls_link,

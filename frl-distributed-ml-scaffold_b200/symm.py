@@ -18,7 +18,7 @@ logger = logging.getLogger(__name__)
 
 class NvlsLink:
     """What the K7 launches need besides the bucket pointers."""
-    __slots__ = ("rank", "world", "pads_dev", "pad_base", "max_blocks", "mc_grad", "mc_out",
+    __slots__ = ("rank", "world", "pads_dev", "pad_base", "max_blocks", "tail_blocks", "mc_grad", "mc_out",
                  "grad_esz", "out_esz", "handles", "scratch", "flags")
 
     def __init__(self):
@@ -71,7 +71,7 @@ def try_make_allocator(device: torch.device, world_size: int) -> Optional[Symmet
 
 
 def make_link(alloc: SymmetricAllocator, grad: torch.Tensor, out: torch.Tensor,
-              max_blocks: int = 32) -> NvlsLink:
+              max_blocks: int = 32, tail_blocks: int = 0) -> NvlsLink:
     hg, ho = alloc.handle_of(grad), alloc.handle_of(out)
     link = NvlsLink()
     link.rank, link.world = hg.rank, hg.world_size
@@ -80,7 +80,10 @@ def make_link(alloc: SymmetricAllocator, grad: torch.Tensor, out: torch.Tensor,
     if hg.signal_pad_size // 4 < 64 or link.world > 32:
         raise RuntimeError("signal pad too small")
     link.max_blocks = max(1, min(max_blocks, 1024))
-    link.scratch = torch.zeros(8 + link.max_blocks, dtype=torch.int32, device=grad.device)
+    # grid of the launch for the bucket that becomes ready LAST: nothing of backward runs beside it
+    # any more, so it may take the SMs the other launches leave to the GEMMs (0 = same grid)
+    link.tail_blocks = max(1, min(tail_blocks, 1024)) if tail_blocks > 0 else link.max_blocks
+    link.scratch = torch.zeros(8 + max(link.max_blocks, link.tail_blocks), dtype=torch.int32, device=grad.device)
     link.mc_grad, link.mc_out = hg.multicast_ptr, ho.multicast_ptr
     link.grad_esz, link.out_esz = grad.element_size(), out.element_size()
     link.handles = [hg, ho]
