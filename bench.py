@@ -363,6 +363,7 @@ def run_torch_gpu(args, rank, local_rank, world, steps, warmup, with_e2e=True, p
         step(*pool[i % 4])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    align_ranks(world, dev)
     e0.record()
     for i in range(steps):
         step(*pool[i % 4])
@@ -406,6 +407,7 @@ def run_torch_gpu(args, rank, local_rank, world, steps, warmup, with_e2e=True, p
         for i in range(3):
             e2e_step(i)
         barrier()
+        align_ranks(world, dev)
         e0.record()
         for i in range(steps):
             e2e_step(i)
@@ -419,6 +421,18 @@ def run_torch_gpu(args, rank, local_rank, world, steps, warmup, with_e2e=True, p
     del net, model, opt, pool
     torch.cuda.empty_cache()
     return res
+
+
+def align_ranks(world, dev):
+    """Device-side barrier enqueued right before a start event (world > 1): a 1-element NCCL
+    all-reduce completes on every GPU when the LAST rank has enqueued it, so the start events of
+    all ranks are recorded within microseconds of one another.  The host barrier before it lets
+    the ranks go up to a millisecond apart (8 GPUs: first timed step 1.86 ms against 1.02 for the
+    rest, all of it one rank waiting at the first exchange for a peer that started later)."""
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        dist.all_reduce(torch.zeros(1, device=dev))
 
 
 def main_torch_gpu(args, rank, local_rank, world):
@@ -689,6 +703,7 @@ def main_b200(args, rank, local_rank, world):
     launches0 = _native.launch_count() + graph_step.REPLAYED_LAUNCHES
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     with ClockSampler(local_rank) as clocks:
+        align_ranks(world, dev)
         marks[0].record()
         host_t0 = time.perf_counter()
         for i in range(K):
@@ -849,6 +864,7 @@ def main_b200(args, rank, local_rank, world):
         barrier()
         m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches_e0 = _native.launch_count() + graph_step.REPLAYED_LAUNCHES
+        align_ranks(world, dev)
         m0.record()
         for ep in range(n_epochs_timed):
             worker.cur_epoch = 2 + ep
@@ -949,6 +965,9 @@ def main_b200(args, rank, local_rank, world):
                            "step_issue": "CUDA graph replay" if args.graph else "eager",
                            "spin_up": "0.25 s GEMM loop on scratch tensors before the warm-up steps (clock ramp of an idle GPU; not a training step)",
                            "parallelism": "dp%d" % world,
+                           "timed_region": "host barrier + synchronize, then (world > 1) a 1-element NCCL all-reduce "
+                                           "enqueued right before the start event so every rank's clock starts "
+                                           "together; K steps; event; host barrier + synchronize; max over ranks",
                            "precision": "bf16 forward/backward + bf16 grads, fp32 master weights and "
                                         "optimizer state" if precision == Precision.BF16 else "fp32",
                            "l2": "no flush needed: each step streams the %.1fM-element arena "
