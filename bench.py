@@ -230,7 +230,9 @@ def main_reference(args, rank):
             "ms_per_step": res["ms_per_step"], "step_p50_ms": res["step_p50_ms"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args, batch), "note": note},
+            # the b200 arm's workload keys (the job this CPU sample stands for) + what was run
+            "config": {"workload": workload_name(args, batch), "global_batch": args.batch * args.gpus,
+                       "parallelism": "dp%d" % args.gpus, "note": note},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
