@@ -563,6 +563,66 @@ def test_lone_bias_bucket_absorbs_its_weight():
         assert lo in slot_of and any(s.end == hi or arena.numel == hi for s in arena.slots)
 
 
+def _random_net(rng):
+    dims = [int(rng.choice([8, 16, 24, 40, 64])) for _ in range(int(rng.integers(2, 6)))]
+    layers = []
+    for a, b in zip(dims[:-1], dims[1:]):
+        layers += [nn.Linear(a, b, bias=bool(rng.integers(0, 2))), nn.ReLU()]
+    return nn.Sequential(*layers[:-1])
+
+
+@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_bucket_and_shard_partition_invariants(double, monkeypatch, seed, world):
+    """Whatever the layer sizes, the cap and the tail split do: launch ranges tile the arena
+    exactly once in reverse order on 8-element boundaries, every parameter knows the buckets it
+    overlaps, and the per-rank shards of every launch range tile that range (what makes
+    ``sync_sharded_state`` and the K7 ownership rule well defined)."""
+    rng = np.random.default_rng(seed)
+    monkeypatch.setenv("FRL_B200_TAIL_SPLIT", "1")
+    monkeypatch.setenv("FRL_B200_TAIL_SPLIT_MIN_BYTES", str(int(rng.choice([0, 256, 1 << 20]))))
+    net = _random_net(rng)
+    arena = ParamArena(net.parameters(), device="cpu",
+                       precision=Precision.BF16 if seed % 2 else Precision.FP32)
+    opt = fused_optim.create_fused_optimizer(arena, OptimOpts(algo=OptAlgorithm.SGD, lr=0.1))
+    pipe = grad_sync.GradBucketPipeline(arena, opt, world_size=world, eager_update=True,
+                                        bucket_cap_mb=float(rng.choice([1e-4, 1e-3, 1.0])),
+                                        first_bucket_mb=None)
+    try:
+        ranges = [(b.lo, b.hi) for b in pipe.buckets]
+        tiled = sorted(ranges)
+        assert tiled[0][0] == 0 and tiled[-1][1] == arena.numel
+        assert all(a[1] == b[0] for a, b in zip(tiled[:-1], tiled[1:]))            # gap-free, no overlap
+        # launch order: last parameters first; the two row blocks of a split weight in row order
+        whole = ranges if not pipe._row_split else ranges[:-2] + [(ranges[-2][0], ranges[-1][1])]
+        assert whole == sorted(whole, reverse=True) and (not pipe._row_split or ranges[-2][1] == ranges[-1][0])
+        assert all(lo % ALIGN_ELEMS == 0 and hi % ALIGN_ELEMS == 0 and lo < hi for lo, hi in ranges)
+        for s in arena.slots:
+            mine = pipe._buckets_of[id(s.param)]
+            assert mine == [b for b in pipe.buckets if s.offset < b.hi and s.end > b.lo]
+            rows = pipe.row_split(s)
+            assert len(mine) == (2 if rows else 1)
+            if rows:                                    # only the first tensor, cut at a row boundary
+                assert s.offset == 0 and mine[0].hi == mine[1].lo == rows * s.shape[1]
+        assert sum(1 for s in arena.slots if pipe.row_split(s)) <= 1
+
+        class _Link:                                    # what shard_of reads of an NvlsLink
+            pass
+        for lo, hi in ranges:
+            cover = []
+            for r in range(world):
+                opt.nvls = _Link()
+                opt.nvls.rank, opt.nvls.world = r, world
+                a, z = opt.shard_of(lo, hi)
+                assert lo <= a <= z <= hi and (a - lo) % ALIGN_ELEMS == 0
+                cover.append((a, z))
+            assert cover[0][0] == lo and max(z for _, z in cover) == hi
+            assert all(x[1] == y[0] or y[0] == y[1] for x, y in zip(cover[:-1], cover[1:]))
+    finally:
+        opt.nvls = None
+        pipe.remove_hooks()
+
+
 def test_quiet_randperm_is_torch_randperm():
     from frl_b200.device_loader import randperm_quiet
     for n in (1, 7, 1000, 100_000):
