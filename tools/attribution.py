@@ -3,6 +3,7 @@
 stock-PyTorch arm, from the per-kernel profiles `bench.py --profile` writes.
 
     python tools/attribution.py profiles/r2j_profile_mlp_b200.json profiles/r2j_profile_mlp_torch.json
+    python tools/attribution.py profiles/r2p_profile_mlp_b200.json profiles/r2p_profile_mlp_b200_e2e.json   # resident vs e2e epoch
 """
 import json
 import sys
@@ -10,6 +11,7 @@ import sys
 GROUPS = [
     ("library GEMM / conv (cuBLAS, cuDNN)", ("nvjet", "gemm", "cutlass", "xmma", "cudnn", "sm80_", "sm90_", "sm100_", "implicit", "wgrad", "dgrad", "fprop")),
     ("gradient exchange (NCCL / K7 / K1)", ("nccl", "nvls_update", "nvls_barrier", "flatten_kernel")),
+    ("input rows over PCIe (K8 / K8w, copy stream)", ("gather_rows", "gather_small_rows", "gather_window_rows")),
     ("optimizer update (K2 / multi_tensor_apply)", ("update_kernel", "update_mt_kernel", "multi_tensor_apply", "FusedSgd", "fused_adam", "FusedAdam")),
     ("criterion (K4 / loss kernels)", ("criteria_", "nll_loss", "log_softmax", "softmax", "mse_", "MseLoss")),
     ("ReLU / bias-gradient / reductions (K6, K6b)", ("colsum", "reduce_kernel", "threshold", "relu", "clamp")),
@@ -47,8 +49,9 @@ def main():
             print("| %s | %.0f (%.0f) | %.0f (%.0f) | %+.0f |" % (g, ga[g][0], ga[g][1], gb[g][0], gb[g][1], gb[g][0] - ga[g][0]))
     print("| **device time, sum** | %.0f | %.0f | %+.0f |" % (sum(v[0] for v in ga.values()), sum(v[0] for v in gb.values()),
                                                             sum(v[0] for v in gb.values()) - sum(v[0] for v in ga.values())))
-    print("| **step (CUDA events)** | %.0f | %.0f | %+.0f |" % (1e3 * a["ms_per_step"], 1e3 * b["ms_per_step"],
-                                                              1e3 * (b["ms_per_step"] - a["ms_per_step"])))
+    if "ms_per_step" in a and "ms_per_step" in b:
+        print("| **step (CUDA events)** | %.0f | %.0f | %+.0f |" % (1e3 * a["ms_per_step"], 1e3 * b["ms_per_step"],
+                                                                  1e3 * (b["ms_per_step"] - a["ms_per_step"])))
 
 
 if __name__ == "__main__":
