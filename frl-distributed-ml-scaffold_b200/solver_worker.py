@@ -497,7 +497,8 @@ class SamplerState:
             if total == 0:
                 return [torch.empty(t.shape, dtype=t.dtype) for t in requests]
             packed = torch.cat(parts)
-            stage = _pinned_block(total)
+            # (host tensors only when a test drives the fold logic without a device)
+            stage = _pinned_block(total) if packed.is_cuda else torch.empty(total, dtype=torch.uint8)
             stage[:total].copy_(packed, non_blocking=True)
             pending.append((stage, packed))               # keep the source alive until the sync
             return [stage[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
@@ -518,7 +519,8 @@ class SamplerState:
         t_q = time.perf_counter()
         landed = flush()
         t_f = time.perf_counter()
-        torch.cuda.current_stream(self._device).synchronize()
+        if self._device.type == "cuda":
+            torch.cuda.current_stream(self._device).synchronize()
         t_s = time.perf_counter()
         pending.clear()
         tracing = bool(os.environ.get("FRL_B200_EPOCH_TRACE"))
